@@ -1,0 +1,1292 @@
+// dca_kernels.cuh -- sm_100a kernels for the haskelldca per-event hot path.
+//
+// One CTA per replica; the replica's whole state (RepState) is staged in shared
+// memory for the duration of the launch and written back once.  Warp 0 runs the
+// event-sequential part of an event (candidate channels, afterstate values,
+// argmax, grid/frep update, event queue, RNG, stats); all warps run the dense
+// average-reward TDC update.  Reference: runStep, src/SimRunner.hs:60-97.
+//
+// All parity-critical fp32/fp64 arithmetic uses explicit round-to-nearest
+// intrinsics (never contracted); the file is also compiled with -fmad=false.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "dca_state.h"
+
+namespace dca {
+
+__constant__ Tables c_tab;
+
+struct RunArgs {
+  RepState* states;
+  int n_replicas;
+  long long max_events;
+  int rng_mode;
+  uint32_t key0, key1;              // Philox key = seed
+  int verify_rc, verify_nb;
+  // tape (RNG_TAPE): per replica offsets into the word / neglog arrays
+  const unsigned long long* tape_words;
+  const double* tape_neglog;
+  const unsigned long long* tape_off;  // [n_replicas + 1]
+  TraceRec* trace;                  // [n_replicas][trace_cap] or null
+  int trace_cap;
+};
+
+// Scratch that lives next to RepState in shared memory.
+struct Scratch {
+  float R[512];    // row sums of x.w   (index f*7 + r)
+  float G[512];    // row sums of x.wg
+  float P[72];     // plane sums of x.w
+  float Pg[72];    // plane sums of x.wg
+  float Gs[16];    // group sums (w)
+  float q[72];     // afterstate values of the candidates
+  uint2 n4b[8];    // row byte masks: N4(cell) \ {cell}
+  uint2 n2b[8];    // row byte masks: N2(cell) u {cell}
+  uint2 chgb[8];   // row byte masks: cells whose n_elig changes (chosen action)
+  unsigned long long n4mask, n2mask, chgmask;
+  unsigned long long hash_grid, hash_frep;
+  float ctd, cavg, cdot, sg;   // TDC scalars of this event
+  float val, dotg, loss;
+  int act_ch, act_diff, ncand, stop;
+  int ev_cell, ev_is_end, ev_type_prev, ev_ch_prev;
+  double ev_time_prev;
+  int flag;
+  uint8_t cand[72];
+};
+
+struct Smem {
+  RepState s;
+  Scratch t;
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// 7 mask bits -> 7 bytes of 0/1 (uint2, byte c = bit c)
+__device__ __forceinline__ uint2 spread7(uint32_t bits) {
+  uint2 r;
+  r.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
+  r.y = (((bits >> 4) & 0x7u) * 0x00204081u) & 0x00010101u;
+  return r;
+}
+// per byte (values < 0x80): 0x01 where byte == k (k in {0,1}), else 0
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t v, uint32_t k) {
+  uint32_t t = v ^ (k * 0x01010101u);
+  return (~(t + 0x7F7F7F7Fu) >> 7) & 0x01010101u;
+}
+__device__ __forceinline__ float byte_f(uint32_t v, int i) {
+  return (float)((v >> (8 * i)) & 0xFFu);
+}
+
+// rowdot of the FAST tree: s = x0*w0; s = fma(x_c, w_c, s), c = 1..6
+__device__ __forceinline__ float rowdot(uint2 xb, float4 wa, float4 wb) {
+  float s = __fmul_rn(byte_f(xb.x, 0), wa.x);
+  s = __fmaf_rn(byte_f(xb.x, 1), wa.y, s);
+  s = __fmaf_rn(byte_f(xb.x, 2), wa.z, s);
+  s = __fmaf_rn(byte_f(xb.x, 3), wa.w, s);
+  s = __fmaf_rn(byte_f(xb.y, 0), wb.x, s);
+  s = __fmaf_rn(byte_f(xb.y, 1), wb.y, s);
+  s = __fmaf_rn(byte_f(xb.y, 2), wb.z, s);
+  return s;
+}
+// tree8 over 8 consecutive lanes (xor butterfly); every lane gets the result
+__device__ __forceinline__ float tree8_lanes(float v) {
+  v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  return v;
+}
+// tree8 of 8 values held by one thread
+__device__ __forceinline__ float tree8(float a0, float a1, float a2, float a3, float a4, float a5,
+                                       float a6, float a7) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)),
+                   __fadd_rn(__fadd_rn(a4, a5), __fadd_rn(a6, a7)));
+}
+
+// ---------------------------------------------------------------------------
+// RNG: Philox4x32-10 (counter = draw index, stream id; key = seed) and the
+// operation-by-operation -log(u) of the Philox mode (DESIGN.md "Random numbers")
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long philox_word(unsigned long long d,
+                                                          unsigned long long stream, uint32_t k0,
+                                                          uint32_t k1) {
+  uint32_t c0 = (uint32_t)d, c1 = (uint32_t)(d >> 32), c2 = (uint32_t)stream,
+           c3 = (uint32_t)(stream >> 32);
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return (unsigned long long)c0 | ((unsigned long long)c1 << 32);
+}
+
+__device__ __noinline__ double neglog_u53(unsigned long long word) {
+  unsigned long long k = word >> 11;
+  if (k == 0) return CUDART_INF;
+  double u = __dmul_rn((double)k, 1.0 / 9007199254740992.0);
+  unsigned long long bits = (unsigned long long)__double_as_longlong(u);
+  int e = (int)((bits >> 52) & 0x7FF) - 1022;
+  bits = (bits & 0x000FFFFFFFFFFFFFULL) | 0x3FE0000000000000ULL;
+  double m = __longlong_as_double((long long)bits);
+  if (m < 0.70710678118654752440) {
+    m = __dadd_rn(m, m);
+    e -= 1;
+  }
+  double s = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0));
+  double z = __dmul_rn(s, s);
+  double p = 1.0 / 21.0;
+  p = __fma_rn(p, z, 1.0 / 19.0);
+  p = __fma_rn(p, z, 1.0 / 17.0);
+  p = __fma_rn(p, z, 1.0 / 15.0);
+  p = __fma_rn(p, z, 1.0 / 13.0);
+  p = __fma_rn(p, z, 1.0 / 11.0);
+  p = __fma_rn(p, z, 1.0 / 9.0);
+  p = __fma_rn(p, z, 1.0 / 7.0);
+  p = __fma_rn(p, z, 1.0 / 5.0);
+  p = __fma_rn(p, z, 1.0 / 3.0);
+  p = __fma_rn(p, z, 1.0);
+  double t = __dmul_rn(s, p);
+  t = __dadd_rn(t, t);
+  return -__fma_rn((double)e, 0.69314718055994530942, t);
+}
+
+// Random source of one replica; all lanes of warp 0 hold identical copies.
+struct Rng {
+  int mode;
+  uint32_t k0, k1;
+  unsigned long long stream;
+  unsigned long long ndraws;
+  const unsigned long long* words;  // tape
+  const double* neglog;
+  unsigned long long tape_len;
+
+  __device__ __forceinline__ unsigned long long idx() const {
+    return (mode == RNG_TAPE && ndraws >= tape_len) ? (tape_len ? tape_len - 1 : 0) : ndraws;
+  }
+  // getRandomWord64 (EventGen/Internal.hs:60)
+  __device__ __forceinline__ unsigned long long word() {
+    unsigned long long w;
+    if (mode == RNG_PHILOX) w = philox_word(ndraws, stream, k0, k1);
+    else w = tape_len ? words[idx()] : 0ULL;
+    ++ndraws;
+    return w;
+  }
+  // getRandomDouble = (w >> 11) / 2^53 (EventGen/Internal.hs:61)
+  __device__ __forceinline__ double uniform() {
+    return __dmul_rn((double)(word() >> 11), 1.0 / 9007199254740992.0);
+  }
+  // random-fu exponential mu = (-log u) * mu, one draw
+  __device__ __forceinline__ double exponential(double mean) {
+    double nl;
+    if (mode == RNG_PHILOX) nl = neglog_u53(word());
+    else {
+      nl = tape_len ? neglog[idx()] : 0.0;
+      ++ndraws;
+    }
+    return __dmul_rn(nl, mean);
+  }
+  // random-fu integralUniform on the low byte, with rejection (EventGen.hs:104)
+  __device__ __forceinline__ int uniform_int(int m) {
+    int n_reject = 256 % m;
+    for (;;) {
+      int z = (int)(word() & 0xFFULL);
+      if (z >= n_reject) return z % m;
+      if (mode == RNG_TAPE && ndraws >= tape_len) return z % m;  // exhausted tape: stop is flagged
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Event queue (warp 0).  Hot scalars are kept uniformly in registers.
+// ---------------------------------------------------------------------------
+struct QRegs {
+  unsigned n_end, next_id;
+};
+
+__device__ __forceinline__ void q_push_new(RepState& s, QRegs& q, int cell, double t) {
+  if (lane_id() == 0) {
+    s.q_time[cell] = t;
+    s.q_id[cell] = q.next_id;
+  }
+  q.next_id++;
+}
+__device__ __forceinline__ void q_push_end(RepState& s, QRegs& q, int cell, int ch, int hoff,
+                                           double t) {
+  unsigned slot = QNEW + q.n_end;
+  if (lane_id() == 0 && slot < QCAP) {
+    s.q_time[slot] = t;
+    s.q_id[slot] = q.next_id;
+    s.q_key[slot] = (uint16_t)((cell << 7) | ch);
+    s.q_hoff[slot] = (uint8_t)hoff;
+  }
+  q.n_end++;
+  q.next_id++;
+}
+// reassign (EventGen.hs:62-72): re-key the END event of (cell, from) to (cell, to)
+__device__ __forceinline__ void q_reassign(RepState& s, const QRegs& q, int cell, int from,
+                                           int to) {
+  const uint16_t want = (uint16_t)((cell << 7) | from);
+  for (unsigned i = QNEW + lane_id(); i < QNEW + q.n_end; i += 32)
+    if (s.q_key[i] == want) s.q_key[i] = (uint16_t)((cell << 7) | to);
+}
+// pop (EventGen.hs:39-50): argmin over (time, id); writes the event into s.ev_*
+__device__ __forceinline__ void q_pop(RepState& s, QRegs& q) {
+  const unsigned total = QNEW + q.n_end;
+  const int lane = lane_id();
+  unsigned long long bt = 0xFFFFFFFFFFFFFFFFULL;
+  unsigned bid = 0xFFFFFFFFu, bslot = 0xFFFFFFFFu;
+  for (unsigned i = lane; i < total; i += 32) {
+    unsigned long long t = (unsigned long long)__double_as_longlong(s.q_time[i]);
+    unsigned id = s.q_id[i];
+    if (t < bt || (t == bt && id < bid)) {
+      bt = t; bid = id; bslot = i;
+    }
+  }
+  // warp argmin with 32-bit redux: time hi, time lo, id
+  unsigned hi = (unsigned)(bt >> 32), lo = (unsigned)bt;
+  unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  bool ok = (hi == mhi);
+  unsigned mlo = __reduce_min_sync(0xffffffffu, ok ? lo : 0xFFFFFFFFu);
+  ok = ok && (lo == mlo);
+  unsigned mid = __reduce_min_sync(0xffffffffu, ok ? bid : 0xFFFFFFFFu);
+  ok = ok && (bid == mid);
+  unsigned src = __ffs(__ballot_sync(0xffffffffu, ok)) - 1;
+  unsigned slot = __shfl_sync(0xffffffffu, bslot, src);
+  if (slot < QNEW) {
+    if (lane == 0) {
+      s.ev_time = s.q_time[slot];
+      s.ev_type = EV_NEW;
+      s.ev_cell = (int)slot;
+      s.ev_ch = -1;
+      s.ev_hoff = HOFF_NONE;
+      s.q_time[slot] = CUDART_INF;
+    }
+  } else {
+    unsigned last = QNEW + q.n_end - 1;
+    if (lane == 0) {
+      unsigned key = s.q_key[slot];
+      s.ev_time = s.q_time[slot];
+      s.ev_type = EV_END;
+      s.ev_cell = (int)(key >> 7);
+      s.ev_ch = (int)(key & 127u);
+      s.ev_hoff = s.q_hoff[slot];
+      if (slot != last) {
+        s.q_time[slot] = s.q_time[last];
+        s.q_id[slot] = s.q_id[last];
+        s.q_key[slot] = s.q_key[last];
+        s.q_hoff[slot] = s.q_hoff[last];
+      }
+    }
+    q.n_end--;
+  }
+  __syncwarp();
+}
+
+// environmentStep (Simulator.hs:101-134) for the current event and action `act`
+// (-1 = Nothing); afterwards s.ev_* holds the next event.  Warp 0 only.
+__device__ __forceinline__ void environment_step(RepState& s, QRegs& q, Rng& rng, int act) {
+  const int lane = lane_id();
+  const int type = s.ev_type, cell = s.ev_cell, ev_ch = s.ev_ch, ev_hoff = s.ev_hoff;
+  const double time = s.ev_time;
+  __syncwarp();
+  if (lane == 0) {  // Stats hooks, Stats.hs:61-81 as called from Simulator.hs:105-114
+    if (type == EV_NEW) {
+      s.stats[6]++; s.stats[0]++;
+      if (act >= 0) s.stats[1]++;
+      else { s.stats[2]++; s.stats[7]++; }
+    } else if (type == EV_HOFF) {
+      s.stats[3]++;
+      if (act < 0) { s.stats[2]++; s.stats[7]++; }  // Simulator.hs:113
+    } else {
+      s.stats[4]++;
+    }
+  }
+  if (type == EV_NEW) {
+    double dt = rng.exponential(s.mean_new);  // generateNewEvent, EventGen.hs:75-85
+    q_push_new(s, q, cell, __dadd_rn(time, dt));
+    if (act >= 0) {
+      double p = rng.uniform();  // Simulator.hs:121, drawn even when hoffProb == 0
+      if (p < s.hoff_prob) {     // generateHoffNewEvent, EventGen.hs:94-109
+        double d2 = rng.exponential(s.call_dur);
+        int m = c_tab.n2cnt[cell];
+        int to = c_tab.n2list[cell][rng.uniform_int(m)];
+        q_push_end(s, q, cell, act, to, __dadd_rn(time, d2));
+        q.next_id++;  // the HOFF event's id (pushed right after its END, never stored)
+      } else {                   // generateEndEvent, EventGen.hs:111-112
+        double d2 = rng.exponential(s.call_dur);
+        q_push_end(s, q, cell, act, HOFF_NONE, __dadd_rn(time, d2));
+      }
+    }
+  } else if (type == EV_HOFF) {
+    if (act >= 0) {              // generateHoffEndEvent, EventGen.hs:114-116
+      double d2 = rng.exponential(s.call_dur_hoff);
+      q_push_end(s, q, cell, act, HOFF_NONE, __dadd_rn(time, d2));
+    }
+  } else {                       // END toCh _, Simulator.hs:129-130
+    if (act >= 0 && act != ev_ch) q_reassign(s, q, cell, act, ev_ch);
+  }
+  __syncwarp();
+  // pop the next event (Simulator.hs:132-134)
+  if (type == EV_END && ev_hoff != HOFF_NONE) {
+    if (lane == 0) {  // the HOFF that follows a hand-off END: same time, next id
+      s.ev_type = EV_HOFF;
+      s.ev_cell = ev_hoff;
+      s.ev_ch = -1;
+      s.ev_hoff = HOFF_NONE;
+    }
+    __syncwarp();
+  } else {
+    q_pop(s, q);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// candidate channels (getAction, Simulator.hs:161-165); warp 0
+// returns n; fills t.cand in ascending channel order (indicesOf, AccUtils.hs:233-240)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int build_candidates(Smem& sm, int cell, bool is_end) {
+  RepState& s = sm.s;
+  const int lane = lane_id();
+  const int pos = c_tab.pos[cell];
+  uint32_t m[3];
+  if (is_end) {  // inuseChs, Gridfuncs.hs:86-87
+    m[0] = s.grid[cell][0]; m[1] = s.grid[cell][1]; m[2] = s.grid[cell][2];
+  } else {       // eligibleChs, Gridfuncs.hs:69-82  <=>  cnt2 == 0
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      int ch = 32 * j + lane;
+      bool e = (ch < NCH) && (s.cnt2[ch * PLANE + pos] == 0);
+      m[j] = __ballot_sync(0xffffffffu, e);
+    }
+  }
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if ((m[j] >> lane) & 1u) sm.t.cand[base + __popc(m[j] & ((1u << lane) - 1u))] = (uint8_t)(32 * j + lane);
+    base += __popc(m[j]);
+  }
+  // row byte masks of the event cell's neighbourhoods
+  const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
+  if (lane < 8) {
+    sm.t.n4b[lane] = (lane < 7) ? spread7((uint32_t)(n4 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
+    sm.t.n2b[lane] = (lane < 7) ? spread7((uint32_t)(n2 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
+  }
+  if (lane == 0) {
+    sm.t.n4mask = n4;
+    sm.t.n2mask = n2;
+  }
+  __syncwarp();
+  return base;
+}
+
+// argpmax (AccUtils.hs:203-208): the largest value, the LAST index among equals.
+// NaNs follow the sequential right fold exactly (rare path).  Warp 0.
+__device__ __forceinline__ int argmax_last(const float* q, int n) {
+  const int lane = lane_id();
+  float bq = -CUDART_INF_F;
+  int bk = -1;
+  bool nan = false;
+  for (int k = lane; k < n; k += 32) {
+    float v = q[k];
+    nan |= (v != v);
+    if (v >= bq) { bq = v; bk = k; }
+  }
+  if (__any_sync(0xffffffffu, nan)) {
+    int best = n - 1;
+    for (int i = n - 2; i >= 0; --i)
+      if (q[i] > q[best]) best = i;
+    return best;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    float oq = __shfl_xor_sync(0xffffffffu, bq, off);
+    int ok = __shfl_xor_sync(0xffffffffu, bk, off);
+    if (oq > bq || (oq == bq && ok > bk)) { bq = oq; bk = ok; }
+  }
+  return bk;
+}
+
+// Which cells change their n_elig feature when `ch` is (de)allocated at the event
+// cell: N2 u {cell} members where ch is eligible on grid' (Gridfuncs.hs:220-232):
+// NEW/HOFF: cnt2 == 0;  END (cell's own use removed): cnt2 == 1.   Warp 0.
+__device__ __forceinline__ unsigned long long elig_change_mask(const RepState& s, int ch,
+                                                               bool is_end,
+                                                               unsigned long long n2mask) {
+  const int lane = lane_id();
+  const uint8_t want = is_end ? 1 : 0;
+  int c0 = lane, c1 = lane + 32;
+  bool b0 = ((n2mask >> c0) & 1ULL) && s.cnt2[ch * PLANE + c_tab.pos[c0]] == want;
+  bool b1 = (c1 < NCELL) && ((n2mask >> c1) & 1ULL) && s.cnt2[ch * PLANE + c_tab.pos[c1]] == want;
+  unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
+  return (unsigned long long)lo | ((unsigned long long)hi << 32);
+}
+
+// executeAction (Gridfuncs.hs:105-110) + in-place frep/cnt2 update to the chosen
+// afterstate (what `ssFrep .= nextFrep` amounts to).  Warp 0.
+__device__ __forceinline__ void apply_action(Smem& sm, int cell, bool is_end, int ch,
+                                             unsigned long long chg) {
+  RepState& s = sm.s;
+  const int lane = lane_id();
+  if (lane < 8) sm.t.chgb[lane] = (lane < 7) ? spread7((uint32_t)(chg >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
+  if (lane == 0) {
+    sm.t.chgmask = chg;
+    uint32_t bit = 1u << (ch & 31);
+    if (is_end) s.grid[cell][ch >> 5] &= ~bit;
+    else s.grid[cell][ch >> 5] |= bit;
+    s.ncalls += is_end ? -1 : 1;
+  }
+  __syncwarp();
+  // three row-parallel updates on lanes 0-6 / 8-14 / 16-22
+  const int r = lane & 7, job = lane >> 3;
+  if (r < 7 && job < 3) {
+    if (job == 0) {  // in-use feature of ch at every cell of N4 \ {cell}: +-1
+      uint2* p = reinterpret_cast<uint2*>(&s.x[ch * PLANE + r * ROWPAD]);
+      uint2 v = *p, d = sm.t.n4b[r];
+      if (is_end) { v.x -= d.x; v.y -= d.y; } else { v.x += d.x; v.y += d.y; }
+      *p = v;
+    } else if (job == 1) {  // n_elig feature: -+1 on the changing cells
+      uint2* p = reinterpret_cast<uint2*>(&s.x[NCH * PLANE + r * ROWPAD]);
+      uint2 v = *p, d = sm.t.chgb[r];
+      if (is_end) { v.x += d.x; v.y += d.y; } else { v.x -= d.x; v.y -= d.y; }
+      *p = v;
+    } else {  // cnt2 of ch over N2 u {cell}
+      uint2* p = reinterpret_cast<uint2*>(&s.cnt2[ch * PLANE + r * ROWPAD]);
+      uint2 v = *p, d = sm.t.n2b[r];
+      if (is_end) { v.x -= d.x; v.y -= d.y; } else { v.x += d.x; v.y += d.y; }
+      *p = v;
+    }
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// FAST order: plane/group sums and afterstate values by substitution
+// ---------------------------------------------------------------------------
+// planes and groups from the row sums R/G; returns val = x.w and dotg = x.wg. Warp 0.
+__device__ __forceinline__ void fast_planes(Smem& sm, float& val, float& dotg) {
+  Scratch& t = sm.t;
+  const int lane = lane_id();
+  for (int f = lane; f < NFEAT; f += 32) {
+    const float* r = &t.R[f * 7];
+    t.P[f] = tree8(r[0], r[1], r[2], r[3], r[4], r[5], r[6], 0.0f);
+    const float* g = &t.G[f * 7];
+    t.Pg[f] = tree8(g[0], g[1], g[2], g[3], g[4], g[5], g[6], 0.0f);
+  }
+  __syncwarp();
+  // lanes 0..9: w groups; lanes 16..25: wg groups
+  float grp = 0.0f;
+  {
+    int g = lane & 15;
+    const float* p = (lane < 16) ? &t.P[7 * g] : &t.Pg[7 * g];
+    if (g < 10) grp = tree8(p[0], p[1], p[2], p[3], p[4], p[5], p[6], 0.0f);
+    if (lane < 10) t.Gs[lane] = grp;
+  }
+  // totals: (tree8(G0..7) + (G8 + G9)) + plane70, for w (lanes 0..15) and wg (16..31)
+  float t8 = tree8_lanes(grp);  // lanes 0-7 / 16-23 hold tree8(G0..G7)
+  float g8 = __shfl_sync(0xffffffffu, grp, (lane & 16) + 8);
+  float g9 = __shfl_sync(0xffffffffu, grp, (lane & 16) + 9);
+  float tot = __fadd_rn(__fadd_rn(t8, __fadd_rn(g8, g9)), (lane < 16) ? t.P[70] : t.Pg[70]);
+  val = __shfl_sync(0xffffffffu, tot, 0);
+  dotg = __shfl_sync(0xffffffffu, tot, 16);
+  __syncwarp();
+}
+
+// q[k] = dense dot of afterstate k in the FAST tree, computed by substituting the
+// two planes the action touches (channel plane ch, n_elig plane 70).  Warp 0;
+// 4 candidates per pass, 8 lanes (7 rows + pad) per candidate.
+__device__ __forceinline__ void fast_qeval(Smem& sm, int n, bool is_end) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const int lane = lane_id(), r = lane & 7, seg = lane >> 3;
+  const bool rv = r < 7;
+  const int rr = rv ? r : 0;
+  const uint32_t want = is_end ? 1u : 0u;
+  // event-constant pieces of this lane's row
+  const uint2 x70 = *reinterpret_cast<const uint2*>(&s.x[NCH * PLANE + rr * ROWPAD]);
+  const float4 w70a = *reinterpret_cast<const float4*>(&s.w[NCH * PLANE + rr * ROWPAD]);
+  const float4 w70b = *reinterpret_cast<const float4*>(&s.w[NCH * PLANE + rr * ROWPAD + 4]);
+  const uint2 n4 = t.n4b[rr], n2 = t.n2b[rr];
+  const float gs_r = t.Gs[r];  // group sums 0..7 for the top-level tree
+  const float gs8 = t.Gs[8], gs9 = t.Gs[9];
+  for (int base = 0; base < n; base += 4) {
+    const int k = base + seg;
+    const bool valid = k < n;
+    const int ch = t.cand[valid ? k : n - 1];
+    // channel plane: x' = x +- [cell in N4]
+    uint2 xr = *reinterpret_cast<const uint2*>(&s.x[ch * PLANE + rr * ROWPAD]);
+    if (is_end) { xr.x -= n4.x; xr.y -= n4.y; } else { xr.x += n4.x; xr.y += n4.y; }
+    const float4 wa = *reinterpret_cast<const float4*>(&s.w[ch * PLANE + rr * ROWPAD]);
+    const float4 wb = *reinterpret_cast<const float4*>(&s.w[ch * PLANE + rr * ROWPAD + 4]);
+    float rowP = rv ? rowdot(xr, wa, wb) : 0.0f;
+    // n_elig plane: e' = e -+ [cell in N2 and ch eligible there on grid']
+    const uint2 cr = *reinterpret_cast<const uint2*>(&s.cnt2[ch * PLANE + rr * ROWPAD]);
+    uint2 er = x70;
+    const uint32_t c0 = n2.x & eq_bytes(cr.x, want), c1 = n2.y & eq_bytes(cr.y, want);
+    if (is_end) { er.x += c0; er.y += c1; } else { er.x -= c0; er.y -= c1; }
+    float rowE = rv ? rowdot(er, w70a, w70b) : 0.0f;
+    const float Pp = tree8_lanes(rowP);
+    const float Ep = tree8_lanes(rowE);
+    // group of ch with plane ch substituted
+    const int gi = ch / 7, ji = ch - 7 * gi;
+    float v = rv ? ((r == ji) ? Pp : t.P[7 * gi + r]) : 0.0f;
+    const float Gp = tree8_lanes(v);
+    // top level with group gi substituted
+    float u = (r == gi) ? Gp : gs_r;
+    const float T8 = tree8_lanes(u);
+    const float g8 = (gi == 8) ? Gp : gs8, g9 = (gi == 9) ? Gp : gs9;
+    const float qv = __fadd_rn(__fadd_rn(T8, __fadd_rn(g8, g9)), Ep);
+    if (r == 0 && valid) t.q[k] = qv;
+  }
+  __syncwarp();
+}
+
+// Row sums R (x.w) and G (x.wg) of the current state; all threads.
+__device__ __forceinline__ void fast_rowsums(Smem& sm) {
+  RepState& s = sm.s;
+  for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
+    const int off = (row / 7) * PLANE + (row % 7) * ROWPAD;
+    const uint2 xb = *reinterpret_cast<const uint2*>(&s.x[off]);
+    const float4 wa = *reinterpret_cast<const float4*>(&s.w[off]);
+    const float4 wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
+    const float4 ga = *reinterpret_cast<const float4*>(&s.wg[off]);
+    const float4 gb = *reinterpret_cast<const float4*>(&s.wg[off + 4]);
+    sm.t.R[row] = rowdot(xb, wa, wb);
+    sm.t.G[row] = rowdot(xb, ga, gb);
+  }
+}
+
+// Dense TDC update (Agent.hs:67-76) fused with the next event's row sums.
+// s.x already holds x' (the afterstate); the pre-action x is rebuilt for the two
+// planes the action touched.  FAST arithmetic:
+//   g = fma(-cdot, x', fma(ctd, x, cavg));  w' = w - g;  wg' = fma(sg, x, wg)
+__device__ __forceinline__ void fast_dense_update(Smem& sm) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const float ctd = t.ctd, cavg = t.cavg, ncdot = -t.cdot, sg = t.sg;
+  const int act_ch = t.act_ch, diff = t.act_diff;
+  for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
+    const int f = row / 7, r = row - 7 * f;
+    const int off = f * PLANE + r * ROWPAD;
+    const uint2 xn = *reinterpret_cast<const uint2*>(&s.x[off]);
+    uint2 xo = xn;
+    if (act_ch >= 0) {
+      if (f == act_ch) {
+        uint2 d = t.n4b[r];
+        if (diff > 0) { xo.x -= d.x; xo.y -= d.y; } else { xo.x += d.x; xo.y += d.y; }
+      } else if (f == NCH) {
+        uint2 d = t.chgb[r];
+        if (diff > 0) { xo.x += d.x; xo.y += d.y; } else { xo.x -= d.x; xo.y -= d.y; }
+      }
+    }
+    float4 wa = *reinterpret_cast<const float4*>(&s.w[off]);
+    float4 wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
+    float4 ga = *reinterpret_cast<const float4*>(&s.wg[off]);
+    float4 gb = *reinterpret_cast<const float4*>(&s.wg[off + 4]);
+    float rs, rg;
+#define DCA_UPD(WV, GV, XN, XO, FIRST)                                   \
+  {                                                                      \
+    const float xnf = (XN), xof = (XO);                                  \
+    const float g_ = __fmaf_rn(ncdot, xnf, __fmaf_rn(ctd, xof, cavg));   \
+    WV = __fsub_rn(WV, g_);                                              \
+    GV = __fmaf_rn(sg, xof, GV);                                         \
+    if (FIRST) { rs = __fmul_rn(xnf, WV); rg = __fmul_rn(xnf, GV); }     \
+    else { rs = __fmaf_rn(xnf, WV, rs); rg = __fmaf_rn(xnf, GV, rg); }   \
+  }
+    DCA_UPD(wa.x, ga.x, byte_f(xn.x, 0), byte_f(xo.x, 0), true)
+    DCA_UPD(wa.y, ga.y, byte_f(xn.x, 1), byte_f(xo.x, 1), false)
+    DCA_UPD(wa.z, ga.z, byte_f(xn.x, 2), byte_f(xo.x, 2), false)
+    DCA_UPD(wa.w, ga.w, byte_f(xn.x, 3), byte_f(xo.x, 3), false)
+    DCA_UPD(wb.x, gb.x, byte_f(xn.y, 0), byte_f(xo.y, 0), false)
+    DCA_UPD(wb.y, gb.y, byte_f(xn.y, 1), byte_f(xo.y, 1), false)
+    DCA_UPD(wb.z, gb.z, byte_f(xn.y, 2), byte_f(xo.y, 2), false)
+#undef DCA_UPD
+    *reinterpret_cast<float4*>(&s.w[off]) = wa;
+    *reinterpret_cast<float4*>(&s.w[off + 4]) = wb;
+    *reinterpret_cast<float4*>(&s.wg[off]) = ga;
+    *reinterpret_cast<float4*>(&s.wg[off + 4]) = gb;
+    t.R[row] = rs;
+    t.G[row] = rg;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// REF order: reference-literal arithmetic (Accelerate Interpreter)
+// ---------------------------------------------------------------------------
+// dense right fold over flatten order i = cell*71 + f, i = 3478..0, of
+// float(afrep[i]) * w[i]; the afterstate of candidate `ch` (or the state itself
+// if ch < 0) is formed on the fly.  One thread.
+__device__ __noinline__ float ref_dense_dot(const Smem& sm, const float* wv, int ch, bool is_end) {
+  const RepState& s = sm.s;
+  const unsigned long long n4 = sm.t.n4mask, n2 = sm.t.n2mask;
+  const int diff = is_end ? -1 : 1;
+  const uint8_t want = is_end ? 1 : 0;
+  float acc = 0.0f;
+  for (int cell = NCELL - 1; cell >= 0; --cell) {
+    const int pos = c_tab.pos[cell];
+    int d_in = 0, d_el = 0;
+    if (ch >= 0) {
+      d_in = ((n4 >> cell) & 1ULL) ? diff : 0;
+      d_el = (((n2 >> cell) & 1ULL) && s.cnt2[ch * PLANE + pos] == want) ? -diff : 0;
+    }
+    for (int f = NFEAT - 1; f >= 0; --f) {
+      int xv = s.x[f * PLANE + pos];
+      if (f == ch) xv += d_in;
+      if (f == NCH) xv += d_el;
+      acc = __fadd_rn(__fmul_rn((float)xv, wv[f * PLANE + pos]), acc);
+    }
+  }
+  return acc;
+}
+
+// elementwise TDC update, Agent.hs:67-76, each operation rounded separately
+__device__ __forceinline__ void ref_dense_update(Smem& sm) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const float ctd = t.ctd, cavg = t.cavg, cdot = t.cdot, sg = t.sg;
+  const int act_ch = t.act_ch, diff = t.act_diff;
+  const unsigned long long n4 = t.n4mask, chg = t.chgmask;
+  for (int i = threadIdx.x; i < NFEAT * NCELL; i += blockDim.x) {
+    const int f = i / NCELL, cell = i - f * NCELL;
+    const int off = f * PLANE + c_tab.pos[cell];
+    const int xn = s.x[off];
+    int xo = xn;
+    if (act_ch >= 0) {
+      if (f == act_ch && ((n4 >> cell) & 1ULL)) xo -= diff;
+      if (f == NCH && ((chg >> cell) & 1ULL)) xo += diff;
+    }
+    const float xnf = (float)xn, xof = (float)xo;
+    const float a1 = __fmul_rn(ctd, xof);
+    const float a3 = __fmul_rn(cdot, xnf);
+    const float g = __fsub_rn(__fadd_rn(a1, cavg), a3);
+    s.w[off] = __fsub_rn(s.w[off], g);
+    s.wg[off] = __fadd_rn(s.wg[off], __fmul_rn(sg, xof));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// hashes for parity traces (order-independent u64 sums); all threads
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ void state_hashes(Smem& sm) {
+  RepState& s = sm.s;
+  unsigned long long hg = 0, hf = 0;
+  for (int i = threadIdx.x; i < NFEAT * NCELL; i += blockDim.x) {
+    const int cell = i / NFEAT, f = i - cell * NFEAT;
+    hf += (unsigned long long)s.x[f * PLANE + c_tab.pos[cell]] * mix64(0x10000ULL + (unsigned long long)i);
+    if (f < NCH && ((s.grid[cell][f >> 5] >> (f & 31)) & 1u)) hg += mix64((unsigned long long)(cell * NCH + f));
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    hg += __shfl_xor_sync(0xffffffffu, hg, off);
+    hf += __shfl_xor_sync(0xffffffffu, hf, off);
+  }
+  if (lane_id() == 0) {
+    atomicAdd(&sm.t.hash_grid, hg);
+    atomicAdd(&sm.t.hash_frep, hf);
+  }
+}
+
+// violatesReuseConstraint (Gridfuncs.hs:94-101) and max(frep) > 70
+// (SimRunner.hs:150,158-159) on the staged state; warp 0.  Returns a status or 0.
+__device__ __forceinline__ int verify_state(const Smem& sm, bool rc, bool nb) {
+  const RepState& s = sm.s;
+  const int lane = lane_id();
+  bool bad_rc = false, bad_nb = false;
+  if (rc) {
+    for (int cell = lane; cell < NCELL; cell += 32) {
+      unsigned long long nbm = c_tab.n2incl[cell] & ~(1ULL << cell);
+      uint32_t o0 = 0, o1 = 0, o2 = 0;
+      while (nbm) {
+        int n = __ffsll((long long)nbm) - 1;
+        nbm &= nbm - 1;
+        o0 |= s.grid[n][0]; o1 |= s.grid[n][1]; o2 |= s.grid[n][2];
+      }
+      bad_rc |= ((o0 & s.grid[cell][0]) | (o1 & s.grid[cell][1]) | (o2 & s.grid[cell][2])) != 0;
+    }
+  }
+  if (nb) {
+    for (int i = lane; i < WPAD; i += 32) bad_nb |= s.x[i] > 70;
+  }
+  if (__any_sync(0xffffffffu, bad_rc)) return ST_REUSE_VIOLATED;
+  if (__any_sync(0xffffffffu, bad_nb)) return ST_NELIG_OVERFLOW;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// state staging
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void stage_in(Smem& sm, const RepState* g) {
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  uint4* dst = reinterpret_cast<uint4*>(&sm.s);
+  for (int i = threadIdx.x; i < (int)(sizeof(RepState) / 16); i += blockDim.x) dst[i] = src[i];
+}
+__device__ __forceinline__ void stage_out(const Smem& sm, RepState* g) {
+  const uint4* src = reinterpret_cast<const uint4*>(&sm.s);
+  uint4* dst = reinterpret_cast<uint4*>(g);
+  for (int i = threadIdx.x; i < (int)(sizeof(RepState) / 16); i += blockDim.x) dst[i] = src[i];
+}
+
+__device__ __forceinline__ Rng make_rng(const RunArgs& a, const RepState& s, int rep) {
+  Rng rng;
+  rng.mode = a.rng_mode;
+  rng.k0 = a.key0;
+  rng.k1 = a.key1;
+  rng.stream = s.stream;
+  rng.ndraws = s.ndraws;
+  rng.words = nullptr;
+  rng.neglog = nullptr;
+  rng.tape_len = 0;
+  if (a.rng_mode == RNG_TAPE && a.tape_off) {
+    unsigned long long o = a.tape_off[rep];
+    rng.words = a.tape_words + o;
+    rng.neglog = a.tape_neglog + o;
+    rng.tape_len = a.tape_off[rep + 1] - o;
+  }
+  return rng;
+}
+
+// ---------------------------------------------------------------------------
+// One event of one replica (runStep, SimRunner.hs:60-97), both orders.
+// Called by every thread of the CTA.  `fixed_*`: step-wise API overrides.
+// ---------------------------------------------------------------------------
+template <int ORDER, bool TRACE>
+__device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, Rng& rng,
+                                          int rep) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const int wid = warp_id(), lane = lane_id();
+  const int nthreads = blockDim.x;
+
+  // ---- accFn1 = getAction (Simulator.hs:154-172) ----
+  if (wid == 0) {
+    const int cell = s.ev_cell;
+    const bool is_end = s.ev_type == EV_END;
+    const int n = build_candidates(sm, cell, is_end);
+    if (lane == 0) {
+      t.ncand = n;
+      t.ev_cell = cell;
+      t.ev_is_end = is_end;
+      t.ev_type_prev = s.ev_type;
+      t.ev_ch_prev = s.ev_ch;
+      t.ev_time_prev = s.ev_time;
+      t.hash_grid = 0;
+      t.hash_frep = 0;
+    }
+    __syncwarp();
+  }
+  if (ORDER == ORDER_REF) {
+    __syncthreads();
+    const int n = t.ncand;
+    const bool is_end = t.ev_is_end;
+    // candidates on threads 0..n-1, V(s) and x.wg on the last two threads
+    for (int k = threadIdx.x; k < n; k += nthreads - 2)
+      if (threadIdx.x < nthreads - 2) t.q[k] = ref_dense_dot(sm, s.w, t.cand[k], is_end);
+    if (threadIdx.x == nthreads - 1) t.val = ref_dense_dot(sm, s.w, -1, false);
+    if (threadIdx.x == nthreads - 2) t.dotg = ref_dense_dot(sm, s.wg, -1, false);
+    __syncthreads();
+  }
+  if (wid == 0) {
+    const int n = t.ncand, cell = t.ev_cell;
+    const bool is_end = t.ev_is_end;
+    float val, dotg;
+    if (ORDER == ORDER_FAST) {
+      fast_planes(sm, val, dotg);
+      if (n > 0) fast_qeval(sm, n, is_end);
+    } else {
+      val = t.val;
+      dotg = t.dotg;
+    }
+    int act = -1;
+    float next_val = val;  // no action: nextFrep = frep (Simulator.hs:170-171)
+    if (n > 0) {
+      const int k = argmax_last(t.q, n);  // selectAction, Simulator.hs:202
+      act = t.cand[k];
+      next_val = t.q[k];
+      const unsigned long long chg = elig_change_mask(s, act, is_end, t.n2mask);
+      apply_action(sm, cell, is_end, act, chg);  // gridStep, Simulator.hs:137-144
+    }
+    // ---- environmentStep (Simulator.hs:101-134) ----
+    environment_step(s, q, rng, act);
+    // ---- backward scalars (Agent.hs:62-67,75,78) ----
+    const float avgR = s.avg_reward;
+    const float reward = (float)s.ncalls;  // boolSum nextGrid
+    const float td = __fsub_rn(__fadd_rn(__fsub_rn(reward, avgR), next_val), val);
+    const float c = __fmul_rn(-2.0f, s.alpha_net);
+    if (lane == 0) {
+      t.ctd = __fmul_rn(c, td);
+      t.cavg = __fmul_rn(c, avgR);
+      t.cdot = __fmul_rn(c, dotg);
+      t.sg = __fmul_rn(s.alpha_grad, __fsub_rn(td, dotg));
+      t.act_ch = act;
+      t.act_diff = is_end ? -1 : 1;
+      t.loss = td;
+      s.avg_reward = __fadd_rn(avgR, __fmul_rn(s.alpha_avg, td));
+      s.iter += 1;  // Simulator.hs:131
+      // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
+      int stop = ST_RUNNING;
+      if (td != td) stop = ST_NAN_LOSS;
+      else {
+        s.loss_sum = __fadd_rn(s.loss_sum, td);
+        s.loss_n += 1;
+      }
+      t.stop = stop;
+    }
+  }
+  __syncthreads();
+  // ---- accFn2's dense part: weight / gradient-correction update ----
+  if (ORDER == ORDER_FAST) fast_dense_update(sm);
+  else ref_dense_update(sm);
+  if (TRACE) state_hashes(sm);
+  __syncthreads();
+  if (wid == 0) {
+    int stop = t.stop;
+    if (stop == ST_RUNNING && (a.verify_rc || a.verify_nb)) {
+      int v = verify_state(sm, a.verify_rc, a.verify_nb);
+      if (v) stop = v;
+    }
+    if (lane == 0) {
+      const float loss = t.loss;
+      if (stop == ST_RUNNING && s.min_loss > 0.0f && s.iter > 50 && fabsf(loss) < s.min_loss)
+        stop = ST_ZERO_LOSS;
+      if (stop == ST_RUNNING && s.iter == s.n_events) stop = ST_SUCCESS;
+      if (stop == ST_RUNNING && a.rng_mode == RNG_TAPE && rng.ndraws + 8 > rng.tape_len)
+        stop = ST_TAPE_EXHAUSTED;
+      s.status = stop;
+      if (TRACE && a.trace && s.iter - 1 < a.trace_cap) {
+        TraceRec& tr = a.trace[(size_t)rep * a.trace_cap + (s.iter - 1)];
+        tr.time = t.ev_time_prev;
+        tr.loss = loss;
+        tr.avg_reward = s.avg_reward;
+        tr.reward = s.ncalls;
+        tr.etype = (uint8_t)t.ev_type_prev;
+        tr.cell = (uint8_t)t.ev_cell;
+        tr.ch = (int8_t)t.act_ch;
+        tr.ncand = (uint8_t)t.ncand;
+        tr.end_ch = (int8_t)(t.ev_is_end ? t.ev_ch_prev : -1);
+        for (int i = 0; i < 7; ++i) tr.pad[i] = 0;
+        tr.grid_hash = t.hash_grid;
+        tr.frep_hash = t.hash_frep;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// The fused run kernel: dca_run.  grid = n_replicas CTAs.
+// ---------------------------------------------------------------------------
+template <int ORDER, bool TRACE>
+__global__ void __launch_bounds__(128) k_run(RunArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int rep = blockIdx.x;
+  if (rep >= a.n_replicas) return;
+  RepState* g = a.states + rep;
+  stage_in(sm, g);
+  __syncthreads();
+  if (!sm.s.initialized || sm.s.status != ST_RUNNING) return;  // uniform
+  if (ORDER == ORDER_FAST) {
+    fast_rowsums(sm);
+    __syncthreads();
+  }
+  QRegs q{sm.s.n_end, sm.s.next_id};
+  Rng rng = make_rng(a, sm.s, rep);
+  for (long long it = 0; it < a.max_events; ++it) {
+    run_event<ORDER, TRACE>(sm, a, q, rng, rep);
+    if (sm.s.status != ST_RUNNING) break;  // uniform after the trailing barrier
+  }
+  if (threadIdx.x == 0) {
+    sm.s.n_end = q.n_end;
+    sm.s.next_id = q.next_id;
+    sm.s.ndraws = rng.ndraws;
+  }
+  __syncthreads();
+  stage_out(sm, g);
+}
+
+// ---------------------------------------------------------------------------
+// mkSimState (Simulator.hs:88-97) on the device: one warp per replica.
+// ---------------------------------------------------------------------------
+struct InitArgs {
+  RepState* states;
+  int n_replicas;
+  int rng_mode;
+  uint32_t key0, key1;
+  unsigned long long first_replica;
+  long long n_events;
+  float min_loss;
+  const double *call_dur, *call_dur_hoff, *mean_new, *hoff_prob;  // per replica
+  const float *alpha_net, *alpha_avg, *alpha_grad;
+  const unsigned long long* tape_words;
+  const double* tape_neglog;
+  const unsigned long long* tape_off;
+  int only_replica;  // >= 0: initialise just this one
+};
+
+__global__ void k_init(InitArgs a) {
+  const int rep = (a.only_replica >= 0) ? a.only_replica : (int)(blockIdx.x * (blockDim.x >> 5) + warp_id());
+  if (rep >= a.n_replicas) return;
+  if (a.only_replica >= 0 && (blockIdx.x != 0 || warp_id() != 0)) return;
+  RepState& s = a.states[rep];
+  const int lane = lane_id();
+  // zero the whole blob (grid, agent, queue, stats)
+  uint4* p = reinterpret_cast<uint4*>(&s);
+  for (int i = lane; i < (int)(sizeof(RepState) / 16); i += 32) p[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  // frep = featureRep emptyGrid: in-use counts 0, n_elig 70 everywhere
+  for (int cell = lane; cell < NCELL; cell += 32) s.x[NCH * PLANE + c_tab.pos[cell]] = NCH;
+  for (int i = lane; i < QCAP; i += 32) {
+    s.q_time[i] = CUDART_INF;
+    s.q_key[i] = (uint16_t)(((i < QNEW ? i : 0) << 7) | 127);
+    s.q_hoff[i] = HOFF_NONE;
+  }
+  __syncwarp();
+  RunArgs ra{};
+  ra.rng_mode = a.rng_mode;
+  ra.key0 = a.key0;
+  ra.key1 = a.key1;
+  ra.tape_words = a.tape_words;
+  ra.tape_neglog = a.tape_neglog;
+  ra.tape_off = a.tape_off;
+  if (lane == 0) {
+    s.stream = a.first_replica + (unsigned long long)rep;
+    s.mean_new = a.mean_new[rep];  // 1/(callRate/60), EventGen.hs:81-82, computed on the host
+    s.call_dur = a.call_dur[rep];
+    s.call_dur_hoff = a.call_dur_hoff[rep];
+    s.hoff_prob = a.hoff_prob[rep];
+    s.alpha_net = a.alpha_net[rep];
+    s.alpha_avg = a.alpha_avg[rep];
+    s.alpha_grad = a.alpha_grad[rep];
+    s.min_loss = a.min_loss;
+    s.n_events = a.n_events;
+    s.status = ST_RUNNING;
+  }
+  __syncwarp();
+  const bool have_rng = a.rng_mode == RNG_PHILOX ||
+                        (a.tape_off && a.tape_off[rep + 1] - a.tape_off[rep] >= (unsigned long long)NCELL);
+  if (!have_rng) {  // tape not set yet: stays uninitialised
+    if (lane == 0) s.initialized = 0;
+    return;
+  }
+  Rng rng = make_rng(ra, s, rep);
+  QRegs q{0u, 0u};
+  // mkEventGen (EventGen.hs:54-58): one NEW per cell, row-major, at 0 + Exp(mean_new)
+  for (int cell = 0; cell < NCELL; ++cell) {
+    double dt = rng.exponential(s.mean_new);
+    q_push_new(s, q, cell, __dadd_rn(0.0, dt));
+  }
+  __syncwarp();
+  q_pop(s, q);  // Simulator.hs:95
+  if (lane == 0) {
+    s.n_end = q.n_end;
+    s.next_id = q.next_id;
+    s.ndraws = rng.ndraws;
+    s.initialized = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// featureRep from scratch (Gridfuncs.hs:153-170) + cnt2, from the grid masks of
+// a replica blob.  One CTA per replica.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void feature_rep_from_grid(RepState& s) {
+  for (int i = threadIdx.x; i < NCH * NCELL; i += blockDim.x) {
+    const int ch = i / NCELL, cell = i - ch * NCELL;
+    const int wsel = ch >> 5, bit = ch & 31;
+    int in4 = 0, in2 = 0;
+    unsigned long long m4 = c_tab.n4excl[cell], m2 = c_tab.n2incl[cell];
+    while (m4) {
+      int n = __ffsll((long long)m4) - 1;
+      m4 &= m4 - 1;
+      in4 += (s.grid[n][wsel] >> bit) & 1u;
+    }
+    while (m2) {
+      int n = __ffsll((long long)m2) - 1;
+      m2 &= m2 - 1;
+      in2 += (s.grid[n][wsel] >> bit) & 1u;
+    }
+    s.x[ch * PLANE + c_tab.pos[cell]] = (uint8_t)in4;
+    s.cnt2[ch * PLANE + c_tab.pos[cell]] = (uint8_t)in2;
+  }
+  __syncthreads();
+  for (int cell = threadIdx.x; cell < NCELL; cell += blockDim.x) {
+    int ne = 0, nc = 0;
+    for (int ch = 0; ch < NCH; ++ch) ne += s.cnt2[ch * PLANE + c_tab.pos[cell]] == 0;
+    nc = __popc(s.grid[cell][0]) + __popc(s.grid[cell][1]) + __popc(s.grid[cell][2]);
+    s.x[NCH * PLANE + c_tab.pos[cell]] = (uint8_t)ne;
+    atomicAdd(&s.ncalls, nc);
+  }
+  __syncthreads();
+}
+
+__global__ void k_feature_rep(RepState* states, int rep) {
+  RepState& s = states[rep];
+  if (threadIdx.x == 0) s.ncalls = 0;
+  __syncthreads();
+  feature_rep_from_grid(s);
+}
+
+// ---------------------------------------------------------------------------
+// Step-wise operators on one replica: accFn1 / accFn2 (SimRunner.hs:61-62).
+// ---------------------------------------------------------------------------
+struct StepOut {
+  int ch;
+  int loss_is_nan;
+  float loss;
+  int pad;
+  long long reward;
+};
+
+// mode 0: getAction -> out->ch.  mode 1: gridStepTrain with the given ch.
+template <int ORDER>
+__global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mode, int cell,
+                                              int is_end_i, int ch_in, float alpha_net,
+                                              float alpha_avg, float alpha_grad, StepOut* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const bool is_end = is_end_i != 0;
+  const int wid = warp_id(), lane = lane_id(), nthreads = blockDim.x;
+  stage_in(sm, states + rep);
+  __syncthreads();
+  if (ORDER == ORDER_FAST) {
+    fast_rowsums(sm);
+    __syncthreads();
+  }
+  if (wid == 0) {
+    const int n = build_candidates(sm, cell, is_end);
+    if (lane == 0) {
+      t.ncand = n;
+      if (mode == 1) {  // evaluate exactly the channel the caller executes
+        t.ncand = ch_in >= 0 ? 1 : 0;
+        t.cand[0] = (uint8_t)(ch_in >= 0 ? ch_in : 0);
+      }
+    }
+  }
+  __syncthreads();
+  const int n = t.ncand;
+  if (ORDER == ORDER_REF) {
+    for (int k = threadIdx.x; k < n; k += nthreads - 2)
+      if (threadIdx.x < nthreads - 2) t.q[k] = ref_dense_dot(sm, s.w, t.cand[k], is_end);
+    if (threadIdx.x == nthreads - 1) t.val = ref_dense_dot(sm, s.w, -1, false);
+    if (threadIdx.x == nthreads - 2) t.dotg = ref_dense_dot(sm, s.wg, -1, false);
+    __syncthreads();
+  }
+  if (wid == 0) {
+    float val, dotg;
+    if (ORDER == ORDER_FAST) {
+      fast_planes(sm, val, dotg);
+      if (n > 0) fast_qeval(sm, n, is_end);
+    } else {
+      val = t.val;
+      dotg = t.dotg;
+    }
+    int act = -1;
+    float next_val = val;
+    if (n > 0) {
+      const int k = argmax_last(t.q, n);
+      act = t.cand[k];
+      next_val = t.q[k];
+    }
+    if (mode == 0) {
+      if (lane == 0) out->ch = act;
+      t.act_ch = -2;  // nothing to apply
+    } else {
+      if (act >= 0) {
+        const unsigned long long chg = elig_change_mask(s, act, is_end, t.n2mask);
+        apply_action(sm, cell, is_end, act, chg);
+      }
+      const float avgR = s.avg_reward;
+      const float reward = (float)s.ncalls;
+      const float td = __fsub_rn(__fadd_rn(__fsub_rn(reward, avgR), next_val), val);
+      const float c = __fmul_rn(-2.0f, alpha_net);
+      if (lane == 0) {
+        t.ctd = __fmul_rn(c, td);
+        t.cavg = __fmul_rn(c, avgR);
+        t.cdot = __fmul_rn(c, dotg);
+        t.sg = __fmul_rn(alpha_grad, __fsub_rn(td, dotg));
+        t.act_ch = act;
+        t.act_diff = is_end ? -1 : 1;
+        s.avg_reward = __fadd_rn(avgR, __fmul_rn(alpha_avg, td));
+        out->ch = act;
+        out->loss = td;
+        out->loss_is_nan = (td != td) ? 1 : 0;
+        out->reward = s.ncalls;
+      }
+    }
+  }
+  __syncthreads();
+  if (mode == 1) {
+    if (ORDER == ORDER_FAST) fast_dense_update(sm);
+    else ref_dense_update(sm);
+    __syncthreads();
+    stage_out(sm, states + rep);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Stateless Gridfuncs operators on explicit arrays (one CTA)
+// ---------------------------------------------------------------------------
+// grid bytes [49][70] -> masks in a scratch RepState
+__global__ void k_gf_load_grid(RepState* st, const uint8_t* grid) {
+  RepState& s = *st;
+  for (int i = threadIdx.x; i < NCELL * 4; i += blockDim.x) (&s.grid[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < WPAD; i += blockDim.x) { s.x[i] = 0; s.cnt2[i] = 0; }
+  if (threadIdx.x == 0) s.ncalls = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < NCELL * NCH; i += blockDim.x) {
+    int cell = i / NCH, ch = i - cell * NCH;
+    if (grid[i]) atomicOr(&s.grid[cell][ch >> 5], 1u << (ch & 31));
+  }
+  __syncthreads();
+  feature_rep_from_grid(s);
+}
+// frep (reference flatten order, int64) out of / into the blob
+__global__ void k_gf_store_frep(const RepState* st, long long* frep) {
+  for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
+    int cell = i / NFEAT, f = i - cell * NFEAT;
+    frep[i] = st->x[f * PLANE + c_tab.pos[cell]];
+  }
+}
+__global__ void k_gf_load_frep(RepState* st, const long long* frep) {
+  for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
+    int cell = i / NFEAT, f = i - cell * NFEAT;
+    st->x[f * PLANE + c_tab.pos[cell]] = (uint8_t)frep[i];
+  }
+}
+// eligible (is_end = 0) / in-use (is_end = 1) channels, ascending
+__global__ void k_gf_chs(const RepState* st, int cell, int is_end, long long* chs, int* n_out) {
+  __shared__ int n;
+  if (threadIdx.x == 0) {
+    n = 0;
+    for (int ch = 0; ch < NCH; ++ch) {
+      bool on = is_end ? ((st->grid[cell][ch >> 5] >> (ch & 31)) & 1u)
+                       : (st->cnt2[ch * PLANE + c_tab.pos[cell]] == 0);
+      if (on) chs[n++] = ch;
+    }
+    *n_out = n;
+  }
+}
+// incAfterStateFreps (Gridfuncs.hs:186-252) in the cnt2 formulation
+__global__ void k_gf_inc_afterstate_freps(const RepState* st, int cell, int is_end,
+                                          const long long* chs, int n, long long* out) {
+  const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
+  const int diff = is_end ? -1 : 1;
+  const uint8_t want = is_end ? 1 : 0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)n * FREP;
+       idx += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(idx / FREP), i = (int)(idx - (long long)k * FREP);
+    int c2 = i / NFEAT, f = i - c2 * NFEAT;
+    int ch = (int)chs[k];
+    int v = st->x[f * PLANE + c_tab.pos[c2]];
+    if (f == ch && ((n4 >> c2) & 1ULL)) v += diff;
+    if (f == NCH && ((n2 >> c2) & 1ULL) && st->cnt2[ch * PLANE + c_tab.pos[c2]] == want) v -= diff;
+    out[idx] = v;
+  }
+}
+__global__ void k_gf_violates(const RepState* st, int* out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  stage_in(sm, st);
+  __syncthreads();
+  if (warp_id() == 0) {
+    int v = verify_state(sm, true, false);
+    if (lane_id() == 0) *out = (v == ST_REUSE_VIOLATED) ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// read-back helpers
+// ---------------------------------------------------------------------------
+struct HostView {  // unpacked replica state in the reference's layouts
+  uint8_t grid[NCELL * NCH];
+  long long frep[FREP];
+  float w[FREP];
+  float wg[FREP];
+};
+__global__ void k_unpack(const RepState* st, HostView* hv) {
+  for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
+    int cell = i / NFEAT, f = i - cell * NFEAT;
+    int off = f * PLANE + c_tab.pos[cell];
+    hv->frep[i] = st->x[off];
+    hv->w[i] = st->w[off];
+    hv->wg[i] = st->wg[off];
+  }
+  for (int i = threadIdx.x; i < NCELL * NCH; i += blockDim.x) {
+    int cell = i / NCH, ch = i - cell * NCH;
+    hv->grid[i] = (st->grid[cell][ch >> 5] >> (ch & 31)) & 1u;
+  }
+}
+// overwrite agent weights from reference-order arrays (either may be null)
+__global__ void k_pack_weights(RepState* st, const float* w, const float* wg) {
+  for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
+    int cell = i / NFEAT, f = i - cell * NFEAT;
+    int off = f * PLANE + c_tab.pos[cell];
+    if (w) st->w[off] = w[i];
+    if (wg) st->wg[off] = wg[i];
+  }
+}
+
+struct Summary {
+  int status;
+  int pad;
+  long long iter;
+  float avg_reward;
+  float loss_sum;
+  long long loss_n;
+  unsigned long long ndraws;
+  long long stats[8];
+};
+__global__ void k_summary(const RepState* states, int n, Summary* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RepState& s = states[i];
+  Summary o;
+  o.status = s.initialized ? s.status : ST_RUNNING;
+  o.pad = 0;
+  o.iter = s.iter;
+  o.avg_reward = s.avg_reward;
+  o.loss_sum = s.loss_sum;
+  o.loss_n = s.loss_n;
+  o.ndraws = s.ndraws;
+  for (int k = 0; k < 8; ++k) o.stats[k] = s.stats[k];
+  out[i] = o;
+}
+// out[0..7] = sum of stats, out[8] = sum of iter, out[9] = replicas that failed
+__global__ void k_sum_stats(const RepState* states, int n, long long* out) {
+  long long acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const RepState& s = states[i];
+    for (int k = 0; k < 8; ++k) acc[k] += s.stats[k];
+    acc[8] += s.iter;
+    acc[9] += (s.status != ST_RUNNING && s.status != ST_SUCCESS) ? 1 : 0;
+  }
+  for (int k = 0; k < 10; ++k) {
+    long long v = acc[k];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane_id() == 0 && v) atomicAdd(reinterpret_cast<unsigned long long*>(&out[k]), (unsigned long long)v);
+  }
+}
+__global__ void k_period_reset(RepState* states, int rep) {
+  RepState& s = states[rep];
+  s.loss_sum = 0.0f;
+  s.loss_n = 0;
+  s.stats[6] = 0;
+  s.stats[7] = 0;
+}
+
+}  // namespace dca

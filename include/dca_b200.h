@@ -1,0 +1,233 @@
+/*
+ * dca_b200.h -- C ABI of libdca_b200.so: the B200 (sm_100a) implementation of
+ * haskelldca's per-event hot path, batched over independent simulator replicas.
+ *
+ * This is the drop-in boundary for the reference's `--backend` dispatch
+ * (src/AccUtils.hs:76-95, src/Base.hs:127-130, src/Opt.hs:90-94).  The reference
+ * has no FFI; its de-facto operator interface is the pair of compiled Accelerate
+ * functions handed to runStep (src/SimRunner.hs:61-62, 211-212):
+ *
+ *   accFn1 = runN bkend getAction      -> dca_get_action
+ *   accFn2 = runN bkend gridStepTrain  -> dca_grid_step_train
+ *
+ * plus the run loop around them (runPeriod, src/SimRunner.hs:132-178, with
+ * environmentStep, src/Simulator.hs:101-134), which the fused kernel replaces
+ * wholesale -> dca_run.  INTEGRATION.md shows the `foreign import ccall`
+ * bindings a maintainer adds to the Haskell modules.
+ *
+ * Conventions: plain C types only; opaque handle owned by the library and
+ * released by dca_destroy; every function returns 0 on success and a negative
+ * DCA_ERR_* otherwise (message via dca_last_error); per-replica *domain*
+ * outcomes (SimStop, src/SimRunner.hs:45-50) are data, not errors; all calls are
+ * synchronous; a handle is not thread-safe, distinct handles are independent.
+ * Host buffers are caller-owned, row-major, fixed width:
+ *   grid  uint8_t[7*7*70]   (Accelerate `Array DIM3 Bool`, src/Base.hs:46)
+ *   frep  int64_t[7*7*71]   (Accelerate `Array DIM3 Int`,  src/Base.hs:51)
+ *   wNet / wGradCorr float[3479], avgReward float (Agent, src/Base.hs:113)
+ * There is no CPU fallback: without a CUDA device dca_create fails.
+ */
+#ifndef DCA_B200_H
+#define DCA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCA_ROWS 7
+#define DCA_COLS 7
+#define DCA_CHANNELS 70
+#define DCA_GRID_SIZE 3430 /* 7*7*70 */
+#define DCA_FREP_SIZE 3479 /* 7*7*71 */
+#define DCA_N_STATS 8
+
+/* error codes */
+#define DCA_OK 0
+#define DCA_ERR_ARG (-1)
+#define DCA_ERR_CUDA (-2)
+#define DCA_ERR_NO_DEVICE (-3)
+#define DCA_ERR_STATE (-4)
+
+/* fp32 reduction order (see DESIGN.md "Arithmetic orders") */
+#define DCA_ORDER_REF 0  /* Accelerate-Interpreter order: dense right folds, no FMA */
+#define DCA_ORDER_FAST 1 /* fixed row/plane/group tree with FMA: the throughput kernel */
+
+/* random source */
+#define DCA_RNG_TAPE 0   /* replay a host-supplied word stream (MT19937-64 for --fixed_rng) */
+#define DCA_RNG_PHILOX 1 /* Philox4x32-10 keyed (seed, replica), counter = draw index */
+
+/* event types, src/Base.hs:67-83 */
+#define DCA_NEW 0
+#define DCA_END 1
+#define DCA_HOFF 2
+
+/* per-replica status = SimStop, src/SimRunner.hs:45-50 */
+#define DCA_RUNNING 0 /* Paused: can run more events */
+#define DCA_SUCCESS 1
+#define DCA_ZERO_LOSS 2
+#define DCA_NAN_LOSS 3
+#define DCA_REUSE_VIOLATED 4
+#define DCA_NELIG_OVERFLOW 5
+#define DCA_TAPE_EXHAUSTED 6 /* DCA_RNG_TAPE ran out of words */
+
+/* stats counters, src/Stats.hs:15-30 */
+#define DCA_ST_ARRIVALS_NEW 0
+#define DCA_ST_ACCEPTED_NEW 1
+#define DCA_ST_REJECTED_NEW 2
+#define DCA_ST_ARRIVALS_HOFF 3
+#define DCA_ST_ENDED 4
+#define DCA_ST_REJECTED_HOFF 5 /* always 0: src/Simulator.hs:113 books hand-off rejects as NEW */
+#define DCA_ST_CURR_ARRIVALS_NEW 6
+#define DCA_ST_CURR_REJECTED_NEW 7
+
+typedef struct dca_handle dca_handle;
+
+/* Mirrors the Opt record (src/Opt.hs:10-25).  Simulation parameters are
+ * per replica: pass arrays of n_replicas values, or NULL to use the scalar. */
+typedef struct {
+  int32_t n_replicas;
+  int32_t device;         /* CUDA device ordinal */
+  uint64_t seed;          /* rngSeed; --fixed_rng => 0 (src/Opt.hs:79-82) */
+  uint64_t first_replica; /* global index of this handle's replica 0 (Philox stream id) */
+  int32_t rng_mode;       /* DCA_RNG_* */
+  int32_t order;          /* DCA_ORDER_* */
+  int64_t n_events;       /* nEvents: a replica stops with DCA_SUCCESS at iter == n_events */
+  float min_loss;         /* minLoss */
+  int32_t verify_reuse_constraint;
+  int32_t verify_nelig_bounds;
+  int32_t trace_capacity; /* per-replica trace records kept (0 = no tracing) */
+  int32_t warps_per_replica; /* 0 = library default */
+  double call_dur, call_dur_hoff, call_rate, hoff_prob; /* callDurNew, callDurHoff, callRate, hoffProb */
+  float alpha_net, alpha_avg, alpha_grad;               /* alphaNet, alphaAvg, alphaGrad */
+  const double *call_dur_v, *call_dur_hoff_v, *call_rate_v, *hoff_prob_v;
+  const float *alpha_net_v, *alpha_avg_v, *alpha_grad_v;
+} dca_config;
+
+/* Event, src/Base.hs:101-105 */
+typedef struct {
+  double time;
+  int32_t etype;          /* DCA_NEW / DCA_END / DCA_HOFF */
+  int32_t r, c;
+  int32_t ch;             /* END: terminating channel, else -1 */
+  int32_t hoff_r, hoff_c; /* END (Just cell), else -1 */
+} dca_event;
+
+/* one record per processed event (trace_capacity > 0); 48 bytes */
+typedef struct {
+  double time;
+  float loss;
+  float avg_reward;
+  int32_t reward;
+  uint8_t etype;
+  uint8_t cell;
+  int8_t ch;
+  uint8_t ncand;
+  int8_t end_ch;
+  uint8_t pad[7];
+  uint64_t grid_hash;
+  uint64_t frep_hash;
+} dca_trace;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+/* Opt defaults, src/Opt.hs:28-76 */
+int dca_config_defaults(dca_config *cfg);
+/* mkSimState for every replica (src/Simulator.hs:88-97): empty grid, zero agent,
+ * frep = featureRep grid, 49 initial NEW events (mkEventGen, src/EventGen.hs:54-58),
+ * first event popped.  In DCA_RNG_TAPE mode initialisation is deferred until the
+ * replica's tape is set. */
+int dca_create(const dca_config *cfg, dca_handle **out);
+int dca_destroy(dca_handle *h);
+/* re-run mkSimState on every replica (same seeds, same parameters) */
+int dca_reset(dca_handle *h);
+/* replace the per-replica simulation parameters (host arrays of n_replicas values,
+ * NULL = keep); they take effect at the next dca_reset */
+int dca_set_params(dca_handle *h, const double *call_dur, const double *call_dur_hoff,
+                   const double *call_rate, const double *hoff_prob, const float *alpha_net,
+                   const float *alpha_avg, const float *alpha_grad);
+const char *dca_last_error(const dca_handle *h);
+int dca_device_count(void);
+
+/* ---- random tape (DCA_RNG_TAPE) ------------------------------------------- */
+/* Replays getRandomWord64 / getRandomDouble (src/EventGen/Internal.hs:57-63):
+ * draw k returns words[k]; exponential draws use neglog[k] = -log((words[k]>>11)/2^53)
+ * computed by the caller's libm so event times match the host bit for bit. */
+int dca_set_rng_tape(dca_handle *h, int32_t replica, const uint64_t *words, const double *neglog,
+                     size_t n);
+/* convenience: generate the tape with MT19937-64 (pureMT seed) + libm log on the host */
+int dca_set_rng_mt19937(dca_handle *h, int32_t replica, uint64_t seed, size_t n_draws);
+
+/* ---- fused run: replaces runPeriod's loop of runStep ------------------------ */
+/* Every replica whose status is DCA_RUNNING processes up to max_events events
+ * (getAction -> environmentStep -> gridStepTrain each) on the device, stopping
+ * early with its own SimStop status.  Returns when the device is done. */
+int dca_run(dca_handle *h, int64_t max_events);
+/* device time of the last dca_run / dca_reset (CUDA events on the launch stream) */
+int dca_elapsed_ms(const dca_handle *h, float *ms);
+int dca_last_launch_count(const dca_handle *h, int64_t *n_kernels);
+
+/* ---- step-wise operators: accFn1 / accFn2 (src/SimRunner.hs:61-62) ---------- */
+/* getAction (src/Simulator.hs:154-172) on the replica's device-resident grid,
+ * frep and agent.  *ch = chosen channel or -1 (Nothing); the afterstate frep is
+ * kept on the device for the following dca_grid_step_train. */
+int dca_get_action(dca_handle *h, int32_t replica, int32_t r, int32_t c, int32_t is_end,
+                   int32_t *ch);
+/* gridStepTrain (src/SimRunner.hs:100-118): execute the action on the grid,
+ * reward = calls in progress, average-reward TDC update (src/Agent.hs:44-81),
+ * then frep := nextFrep (src/SimRunner.hs:88-90). */
+int dca_grid_step_train(dca_handle *h, int32_t replica, float alpha_net, float alpha_avg,
+                        float alpha_grad, int32_t is_end, int32_t r, int32_t c, int32_t ch,
+                        float *loss, int32_t *loss_is_nan, int64_t *reward);
+
+/* ---- state read-back / write ----------------------------------------------- */
+/* any output pointer may be NULL */
+int dca_read_state(dca_handle *h, int32_t replica, uint8_t *grid, int64_t *frep, float *wnet,
+                   float *wgrad, float *avg_reward, int64_t *iter, dca_event *next_event);
+/* overwrite grid and/or agent; frep is recomputed with featureRep (src/Gridfuncs.hs:153-170).
+ * Pending END events are NOT rebuilt: meant for step-wise use and tests. */
+int dca_write_state(dca_handle *h, int32_t replica, const uint8_t *grid, const float *wnet,
+                    const float *wgrad, const float *avg_reward);
+int dca_read_stats(dca_handle *h, int32_t replica, int64_t stats[DCA_N_STATS]);
+int dca_read_status(dca_handle *h, int32_t replica, int32_t *status, int64_t *iter,
+                    uint64_t *n_draws);
+/* sum of losses (fp32, in event order) and their count since the last reset;
+ * reset also clears the period counters like statsReportPeriod (src/Stats.hs:117-118) */
+int dca_read_period(dca_handle *h, int32_t replica, float *loss_sum, int64_t *n, int32_t reset);
+int dca_read_trace(dca_handle *h, int32_t replica, dca_trace *out, size_t cap, size_t *n);
+/* bulk: per-replica arrays of length n_replicas (any may be NULL) */
+int dca_read_summary(dca_handle *h, int32_t *status, int64_t *iter, float *avg_reward,
+                     int64_t *stats /* [n_replicas][8] */);
+/* device-side sum over replicas: out[0..7] = stats, out[8] = events processed,
+ * out[9] = replicas not RUNNING/SUCCESS.  *dev_ptr (optional) receives the device
+ * address of the same int64[10] so a caller can all-reduce it across GPUs (NCCL). */
+int dca_sum_stats(dca_handle *h, int64_t out[10], void **dev_ptr);
+/* Stats.hs:83-92 */
+void dca_stats_cumus(const int64_t stats[DCA_N_STATS], double out3[3]);
+
+/* ---- Gridfuncs / Gridneighs operators on explicit host arrays --------------- */
+/* Stateless device implementations of the reference's grid functions, for
+ * callers and tests that work on arrays rather than a replica handle. */
+int dca_get_neighs(int32_t d, int32_t r, int32_t c, int32_t include_self, int32_t *out_rc,
+                   int32_t *n);                                  /* Gridneighs.hs:92-98 */
+int dca_gf_eligible_chs(int32_t device, const uint8_t *grid, int32_t r, int32_t c, int64_t *chs,
+                        int32_t *n);                             /* Gridfuncs.hs:81-82 */
+int dca_gf_inuse_chs(int32_t device, const uint8_t *grid, int32_t r, int32_t c, int64_t *chs,
+                     int32_t *n);                                /* Gridfuncs.hs:86-87 */
+int dca_gf_feature_rep(int32_t device, const uint8_t *grid, int64_t *frep); /* :153-170 */
+int dca_gf_inc_afterstate_freps(int32_t device, int32_t r, int32_t c, int32_t is_end,
+                                const int64_t *chs, int32_t n, const uint8_t *grid,
+                                const int64_t *frep, int64_t *freps_out);   /* :186-252 */
+int dca_gf_violates_reuse_constraint(int32_t device, const uint8_t *grid, int32_t *violates);
+                                                                            /* :94-101 */
+
+/* ---- multi-GPU (one handle per device, one process or many) ------------------ */
+/* Sum the int64[10] of dca_sum_stats over several handles of THIS process with
+ * ncclAllReduce (ncclCommInitAll).  With one process per GPU, all-reduce the
+ * dev_ptr of dca_sum_stats with the caller's own communicator instead. */
+int dca_allreduce_stats(dca_handle **handles, int32_t n, int64_t out[10]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCA_B200_H */

@@ -325,25 +325,36 @@ static float dot_ref(const int64_t *x, const float *w) {
   return acc;
 }
 
-/* FAST canonical tree (see header). Flatten index i = (r*7+c)*71 + f. */
+/* FAST canonical tree (see header). Flatten index i = (r*7+c)*71 + f.
+ *   rowdot(f,r) = fma chain over the 7 columns (first term a plain product)
+ *   tree8(a0..a7) = ((a0+a1)+(a2+a3)) + ((a4+a5)+(a6+a7))
+ *   plane(f)  = tree8(rowdot(f,0..6), 0)
+ *   group(g)  = tree8(plane(7g..7g+6), 0),  g = 0..9
+ *   dot       = (tree8(group(0..7)) + (group(8)+group(9))) + plane(70)
+ * (an xor-butterfly over 8 lanes computes tree8 in 3 shuffle steps). */
+static float tree8(const float a[8]) {
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
 static float rowdot_fast(const int64_t *x, const float *w, int f, int r) {
   float s = (float)x[FIDX(r, 0, f)] * w[FIDX(r, 0, f)];
   for (int c = 1; c < C_; ++c) s = fmaf((float)x[FIDX(r, c, f)], w[FIDX(r, c, f)], s);
   return s;
 }
 static float plane_fast(const int64_t *x, const float *w, int f) {
-  float p = rowdot_fast(x, w, f, 0);
-  for (int r = 1; r < R_; ++r) p = p + rowdot_fast(x, w, f, r);
-  return p;
+  float a[8];
+  for (int r = 0; r < R_; ++r) a[r] = rowdot_fast(x, w, f, r);
+  a[7] = 0.0f;
+  return tree8(a);
 }
 static float dot_fast(const int64_t *x, const float *w) {
-  float total = 0.0f;
+  float grp[10];
   for (int g = 0; g < 10; ++g) {
-    float grp = plane_fast(x, w, 7 * g);
-    for (int j = 1; j < 7; ++j) grp = grp + plane_fast(x, w, 7 * g + j);
-    total = (g == 0) ? grp : total + grp;
+    float a[8];
+    for (int j = 0; j < 7; ++j) a[j] = plane_fast(x, w, 7 * g + j);
+    a[7] = 0.0f;
+    grp[g] = tree8(a);
   }
-  return total + plane_fast(x, w, CH_);
+  return (tree8(grp) + (grp[8] + grp[9])) + plane_fast(x, w, CH_);
 }
 
 float orc_dense_dot(int order, const int64_t *frep, const float *w) {

@@ -26,8 +26,9 @@
  *                    x0+(x1+(...+(x_{n-1}+0))) in flatten order, products and
  *                    sums rounded separately, no FMA.
  *   ORC_ORDER_FAST : the same dense dots re-associated into a fixed tree
- *                    (7-col row chains with FMA -> 7-row plane sums -> groups of
- *                    7 channel planes -> total + n_elig plane) and the TDC
+ *                    (7-col row chains with FMA -> tree8 over the 7 rows of a
+ *                    feature plane -> tree8 over groups of 7 channel planes ->
+ *                    total + n_elig plane; see dot_fast) and the TDC
  *                    update written with explicit FMAs.  Accelerate's `fold`
  *                    requires an associative operator and leaves the order
  *                    unspecified, so this is a legal execution of the same

@@ -1,0 +1,264 @@
+"""GPU parity: libdca_b200 (through the C ABI) vs the CPU oracle.  Run with -m gpu on a B200.
+
+Bar: grid, frep, chosen channels, event stream bit-exact; weights, average reward and loss
+bit-exact too (the oracle fixes the fp32 order per mode) -- a fortiori within the 1e-4
+relative tolerance BASELINE.json's north_star states.
+"""
+import numpy as np
+import pytest
+
+import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+TRACE_EXACT = ("etype", "cell", "ch", "ncand", "end_ch", "reward", "time", "grid_hash", "frep_hash")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_trace_equal(got, want):
+    assert len(got) == len(want)
+    for k in TRACE_EXACT:
+        bad = np.flatnonzero(got[k] != want[k])
+        assert bad.size == 0, f"trace field {k} first differs at event {bad[0]}: {got[k][bad[0]]} vs {want[k][bad[0]]}"
+    for k in ("loss", "avg_reward"):
+        bad = np.flatnonzero(bits(got[k]) != bits(want[k]))
+        assert bad.size == 0, f"trace field {k} first differs at event {bad[0]}: {got[k][bad[0]]} vs {want[k][bad[0]]}"
+
+
+def assert_state_equal(got, want, rel=None):
+    for k in ("grid", "frep", "stats"):
+        assert np.array_equal(got[k], want[k]), k
+    assert got["iter"] == want["iter"]
+    assert got["event"] == want["event"]
+    for k in ("w", "wg"):
+        assert np.array_equal(bits(got[k]), bits(want[k])), k
+        np.testing.assert_allclose(got[k], want[k], rtol=1e-4)  # the stated fp32 tolerance, implied by bit equality
+    assert bits(got["avg_reward"]) == bits(want["avg_reward"])
+
+
+def oracle_run(order, n_events, seed=0, hoff=0.0, rng=po.RNG_MT, replica=0, **kw):
+    o = po.Sim(po.default_opt(order=order, rng_mode=rng, seed=seed, replica=replica, n_events=n_events, hoff_prob=hoff, **kw))
+    status, done, tr = o.run(n_events, trace=True)
+    return o, status, tr
+
+
+@pytest.mark.parametrize("order,oorder", [("ref", po.ORDER_REF), ("fast", po.ORDER_FAST)])
+def test_config1_fixed_rng_replay_10k(order, oorder):
+    """BASELINE config 1: 7x7x70, 200/h, 3 min, hoff 0, 10 000 events, --fixed_rng (MT19937-64 seed 0)."""
+    from haskelldca_b200 import Opt, Replicas
+
+    n = 10000
+    o, status, tr = oracle_run(oorder, n)
+    with Replicas(Opt(n_events=n, order=order, rng="mt19937", rng_seed=0, trace=n)) as sims:
+        sims.run(n)
+        assert sims.read_status(0)[0] == status == po.SUCCESS
+        assert sims.read_status(0)[2] == o.ndraws
+        assert_trace_equal(sims.read_trace(0), tr)
+        got, want = sims.read_state(0), o.read()
+        assert_state_equal(got, want)
+        bp_got = got["stats"][2] / (got["stats"][0] + 1.0)
+        assert bp_got == pytest.approx(po.stats_cumus(want["stats"])[0], rel=1e-4)
+
+
+@pytest.mark.parametrize("order,oorder,n", [("ref", po.ORDER_REF, 30000), ("fast", po.ORDER_FAST, 100000)])
+def test_config2_handoffs(order, oorder, n):
+    """BASELINE config 2: hoff_prob 0.15, call_dur_hoff 1 (100 000 events; the reference-order kernel on a 30k prefix)."""
+    from haskelldca_b200 import Opt, Replicas
+
+    o, status, tr = oracle_run(oorder, n, hoff=0.15)
+    with Replicas(Opt(n_events=n, order=order, rng="mt19937", rng_seed=0, hoff_prob=0.15, trace=n)) as sims:
+        sims.run(n)
+        assert sims.read_status(0)[0] == status
+        assert_trace_equal(sims.read_trace(0), tr)
+        assert_state_equal(sims.read_state(0), o.read())
+    assert (tr["etype"] == po.HOFF).sum() > 500
+
+
+def test_run_in_periods_equals_one_run():
+    from haskelldca_b200 import Opt, Replicas
+
+    n = 3000
+    o, _, tr = oracle_run(po.ORDER_FAST, n, hoff=0.1)
+    with Replicas(Opt(n_events=n, order="fast", rng="mt19937", rng_seed=0, hoff_prob=0.1, trace=n)) as sims:
+        for _ in range(6):
+            sims.run(500)  # runPeriod-sized chunks (SimRunner.hs:167-168)
+        assert sims.read_status(0)[0] == po.SUCCESS
+        assert_trace_equal(sims.read_trace(0), tr)
+        assert_state_equal(sims.read_state(0), o.read())
+        sims.run(500)  # a finished replica does not move
+        assert sims.read_status(0)[1] == n
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4])
+def test_philox_replicas_match_oracle(warps):
+    """Config 3's RNG mode on a small batch: every replica equals its own oracle run, for any CTA width."""
+    from haskelldca_b200 import Opt, Replicas
+
+    n_rep, n_ev = 24, 1500
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=42, hoff_prob=0.15,
+                      first_replica=1000, trace=n_ev, warps_per_replica=warps)) as sims:
+        sims.run(n_ev)
+        summ = sims.read_summary()
+        assert (summ["status"] == po.SUCCESS).all() and (summ["iter"] == n_ev).all()
+        for r in range(n_rep):
+            o, _, tr = oracle_run(po.ORDER_FAST, n_ev, seed=42, hoff=0.15, rng=po.RNG_PHILOX, replica=1000 + r)
+            assert_trace_equal(sims.read_trace(r), tr)
+            assert_state_equal(sims.read_state(r), o.read())
+        total, dev = sims.sum_stats()
+        assert total[8] == n_rep * n_ev and total[9] == 0 and dev
+        assert np.array_equal(total[:8], summ["stats"].sum(axis=0))
+
+
+def test_philox_ref_order_matches_oracle():
+    from haskelldca_b200 import Opt, Replicas
+
+    n_rep, n_ev = 4, 600
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="ref", rng="philox", rng_seed=5, hoff_prob=0.2, trace=n_ev)) as sims:
+        sims.run(n_ev)
+        for r in range(n_rep):
+            o, _, tr = oracle_run(po.ORDER_REF, n_ev, seed=5, hoff=0.2, rng=po.RNG_PHILOX, replica=r)
+            assert_trace_equal(sims.read_trace(r), tr)
+            assert_state_equal(sims.read_state(r), o.read())
+
+
+def test_per_replica_parameters():
+    """Config 5's shape: call_rate x learning-rate grid as per-replica arrays."""
+    from haskelldca_b200 import Opt, Replicas
+
+    rates = [150.0, 200.0, 250.0, 300.0]
+    lrs = [(2.52e-6, 0.06, 5e-6), (1e-6, 0.03, 1e-6)]
+    grid = [(r, lr) for r in rates for lr in lrs]
+    n_ev = 1200
+    per = dict(call_rate=[g[0] for g in grid], learning_rate=[g[1][0] for g in grid],
+               learning_rate_avg=[g[1][1] for g in grid], learning_rate_grad=[g[1][2] for g in grid])
+    with Replicas(Opt(n_replicas=len(grid), n_events=n_ev, order="fast", rng="philox", rng_seed=9), per_replica=per) as sims:
+        sims.run(n_ev)
+        for i, (rate, lr) in enumerate(grid):
+            o = po.Sim(po.default_opt(order=po.ORDER_FAST, rng_mode=po.RNG_PHILOX, seed=9, replica=i, n_events=n_ev,
+                                      call_rate=rate, alpha_net=lr[0], alpha_avg=lr[1], alpha_grad=lr[2]))
+            o.run(n_ev)
+            assert_state_equal(sims.read_state(i), o.read())
+        # set_params + reset: all replicas at 300/h
+        nb = sims.set_params(call_rate=[300.0] * len(grid))
+        assert nb == 8 * len(grid)
+        sims.reset()
+        sims.run(n_ev)
+        o = po.Sim(po.default_opt(order=po.ORDER_FAST, rng_mode=po.RNG_PHILOX, seed=9, replica=1, n_events=n_ev,
+                                  call_rate=300.0, alpha_net=grid[1][1][0], alpha_avg=grid[1][1][1], alpha_grad=grid[1][1][2]))
+        o.run(n_ev)
+        assert_state_equal(sims.read_state(1), o.read())
+
+
+def test_reset_reproduces_the_run():
+    from haskelldca_b200 import Opt, Replicas
+
+    with Replicas(Opt(n_replicas=16, n_events=800, order="fast", rng="philox", rng_seed=3)) as sims:
+        sims.run(800)
+        a = sims.read_summary()
+        w0 = sims.read_state(5)["w"].copy()
+        sims.reset()
+        assert (sims.read_summary()["iter"] == 0).all()
+        sims.run(800)
+        b = sims.read_summary()
+        assert np.array_equal(a["stats"], b["stats"]) and np.array_equal(bits(a["avg_reward"]), bits(b["avg_reward"]))
+        assert np.array_equal(bits(w0), bits(sims.read_state(5)["w"]))
+
+
+def test_stepwise_operators_follow_the_oracle_event_stream():
+    """accFn1/accFn2 through dca_get_action / dca_grid_step_train with the host keeping the event generator
+    (the reference's runStep shape, SimRunner.hs:60-97)."""
+    from haskelldca_b200 import Opt, Replicas
+
+    for order, oorder in (("ref", po.ORDER_REF), ("fast", po.ORDER_FAST)):
+        n = 250
+        o, _, tr = oracle_run(oorder, n, hoff=0.15)
+        with Replicas(Opt(n_events=n, order=order, rng="philox")) as sims:  # the device queue is not used here
+            for i in range(n):
+                cell = (int(tr["cell"][i]) // 7, int(tr["cell"][i]) % 7)
+                is_end = tr["etype"][i] == po.END
+                ch = sims.get_action(0, cell, is_end)
+                assert ch == tr["ch"][i], (order, i)
+                loss, isnan, reward = sims.grid_step_train(0, is_end, cell, ch)
+                assert bits(loss) == bits(tr["loss"][i]) and not isnan and reward == tr["reward"][i], (order, i)
+            got, want = sims.read_state(0), o.read()
+            for k in ("grid", "frep"):
+                assert np.array_equal(got[k], want[k])
+            for k in ("w", "wg"):
+                assert np.array_equal(bits(got[k]), bits(want[k]))
+            assert bits(got["avg_reward"]) == bits(want["avg_reward"])
+
+
+def test_stop_rules_and_status_words():
+    from haskelldca_b200 import Opt, Replicas, _ffi
+
+    with Replicas(Opt(n_replicas=3, n_events=1000, min_loss=1e9, order="fast")) as sims:  # ZeroLoss, SimRunner.hs:161
+        sims.run(1000)
+        s = sims.read_summary()
+        assert (s["status"] == _ffi.ZERO_LOSS).all() and (s["iter"] == 51).all()
+    with Replicas(Opt(n_replicas=2, n_events=100, order="fast", verify_reuse_constraint=True, verify_nelig_bounds=True)) as sims:
+        sims.run(1000)
+        s = sims.read_summary()
+        assert (s["status"] == _ffi.SUCCESS).all() and (s["iter"] == 100).all()
+    with Replicas(Opt(n_replicas=2, n_events=500, order="fast")) as sims:  # NaNLoss, Agent.hs:80 / SimRunner.hs:152
+        sims.run(100)
+        w = sims.read_state(1)["w"]
+        w[:] = np.nan
+        sims.write_state(1, w=w)
+        sims.run(400)
+        s = sims.read_summary()
+        assert s["status"].tolist() == [_ffi.SUCCESS, _ffi.NAN_LOSS] and s["iter"].tolist() == [500, 101]
+        assert sims.sum_stats()[0][9] == 1
+    with Replicas(Opt(n_events=5000, order="fast", rng="mt19937")) as sims:  # tape shorter than the run
+        sims.set_rng_mt19937(0, 0, 600)
+        sims.run(5000)
+        st, it, nd = sims.read_status(0)
+        assert st == _ffi.TAPE_EXHAUSTED and 100 < it < 600 and nd <= 600
+    # a corrupted grid trips the reuse-constraint check (SimRunner.hs:155-156)
+    with Replicas(Opt(n_events=50, order="fast", verify_reuse_constraint=True)) as sims:
+        g = np.zeros((7, 7, 70), np.uint8)
+        g[3, 3, 5] = g[3, 4, 5] = 1
+        sims.write_state(0, grid=g)
+        sims.run(10)
+        assert sims.read_status(0) [0] == _ffi.REUSE_VIOLATED and sims.read_status(0)[1] == 1
+
+
+def test_period_accumulators():
+    from haskelldca_b200 import Opt, Replicas
+
+    n = 1000
+    o, _, tr = oracle_run(po.ORDER_FAST, n)
+    with Replicas(Opt(n_events=3000, order="fast", rng="mt19937", log_iter=n)) as sims:
+        sims.run(n)
+        lsum, ln = sims.read_period(0, reset=True)
+        want_sum, want_n = o.period(reset=False)
+        assert ln == want_n == n and bits(lsum) == bits(want_sum)
+        st = sims.read_stats(0)
+        assert st[6] == 0 and st[7] == 0 and st[0] == o.read()["stats"][0]
+        assert sims.read_period(0)[1] == 0
+
+
+def test_invariants_at_scale():
+    """Size-independent properties on a larger batch (Stats.hs:139-147 call conservation, reuse constraint,
+    incremental frep == featureRep, event counts)."""
+    from haskelldca_b200 import Opt, Replicas, gridfuncs
+
+    n_rep, n_ev = 1024, 4000
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=11, hoff_prob=0.15)) as sims:
+        ms = sims.run(n_ev)
+        s = sims.read_summary()
+        assert (s["status"] == po.SUCCESS).all() and (s["iter"] == n_ev).all() and ms > 0
+        st = s["stats"]
+        in_progress = st[:, 0] + st[:, 3] - st[:, 2] - st[:, 5] - st[:, 4]
+        assert (st[:, 5] == 0).all() and (st[:, 0] + st[:, 3] + st[:, 4] == n_ev).all()
+        assert len(np.unique(s["avg_reward"])) > n_rep // 2
+        for r in (0, 1, 511, 1023):
+            x = sims.read_state(r)
+            assert x["grid"].sum() == in_progress[r]
+            assert not gridfuncs.violates_reuse_constraint(x["grid"])
+            assert np.array_equal(x["frep"], po.feature_rep(x["grid"]))
+            assert np.array_equal(gridfuncs.feature_rep(x["grid"]), x["frep"])
+        bp = st[:, 2].sum() / (st[:, 0].sum() + 1.0)
+        assert 0.02 < bp < 0.4

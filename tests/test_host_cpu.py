@@ -1,0 +1,84 @@
+"""CPU-side checks of the product's host layer: C-ABI exports, Opt parser, report strings."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from haskelldca_b200 import _ffi
+
+    L = _ffi.load()
+    hdr = open(os.path.join(ROOT, "include", "dca_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dca_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    assert declared == set(_ffi.SYMBOLS), declared ^ set(_ffi.SYMBOLS)
+    for name in declared:
+        assert getattr(L, name) is not None
+
+
+def test_no_device_fails_loudly_instead_of_falling_back():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from haskelldca_b200 import Opt, Replicas, _ffi, gridfuncs
+
+    with pytest.raises(_ffi.DcaError, match="no CUDA device"):
+        Replicas(Opt())
+    with pytest.raises(_ffi.DcaError, match="no CUDA device"):
+        gridfuncs.feature_rep(gridfuncs.mk_grid())
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "haskelldca_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in src and "dca_oracle" not in src and "oracle/" not in src, f
+
+
+def test_neighbourhood_tables_host_side():
+    import pyoracle as po
+    from haskelldca_b200 import gridneighs
+
+    assert gridneighs.get_neighs(1, (3, 3), False) == [(3, 2), (4, 2), (4, 3), (3, 4), (2, 4), (2, 3)]
+    for cell in [(0, 0), (3, 3), (6, 2), (4, 5)]:
+        for d in (1, 2, 3, 4):
+            assert gridneighs.get_neighs(d, cell, True) == po.get_neighs(d, *cell, True)
+
+
+def test_opt_defaults_and_flags():  # src/Opt.hs:28-94
+    from haskelldca_b200 import get_opts
+
+    o = get_opts([], rand=1234)
+    assert (o.call_dur, o.call_dur_hoff, o.call_rate, o.hoff_prob) == (3.0, 1.0, 200.0, 0.0)
+    assert (o.n_events, o.log_iter) == (10000, 1000)
+    assert (o.learning_rate, o.learning_rate_avg, o.learning_rate_grad, o.min_loss) == (2.52e-6, 0.06, 5e-6, 0.0)
+    assert o.rng_seed == 1234 and not o.verify_reuse_constraint and not o.verify_nelig_bounds
+    o = get_opts("--fixed_rng --hoff_prob 0.15 --n_events 100000 --call_rate 250 --verify_reuse_constraint --backend gpu".split(), rand=99)
+    assert o.rng_seed == 0 and o.hoff_prob == 0.15 and o.n_events == 100000 and o.call_rate == 250 and o.verify_reuse_constraint
+    with pytest.raises(SystemExit):
+        get_opts(["--backend", "interp"])
+
+
+def test_stats_reports_format():  # src/Stats.hs:83-152
+    from haskelldca_b200 import _ffi, stats
+
+    st = np.array([5520, 4913, 607, 0, 4480, 0, 540, 61], dtype=np.int64)
+    new, hoff, tot = stats.stats_cumus(st)
+    assert new == 607 / 5521 and hoff == 0 and tot == 607 / 5521
+    out = np.zeros(3)
+    _ffi.load().dca_stats_cumus(_ffi.ptr(st), _ffi.ptr(out))
+    assert out.tolist() == [new, hoff, tot]
+    s = stats.stats_report_period(st, 10000, 1000, np.float32(-1234.5), 1000, 333.85226)
+    assert s == "Blocking probability events 9000-10000: 0.1128, cumulative 0.1099, avg. loss: -1.2, avg. reward 333.8523"
+    e = stats.stats_report_end(st, 433, 10000)
+    assert e.startswith("Finished 10000 events. Blocking probability 0.1099 for new calls.\n5520 new arrivals of which 607 have been rejected. 433 calls in progress")
+    assert "SOME CALLS WERE LOST" not in e
+    assert "SOME CALLS WERE LOST" in stats.stats_report_end(st, 432, 10000)

@@ -49,18 +49,15 @@ def test_dense_dot_fast_tree():
             s = fma(x[r, c, fe], w3[r, c, fe], s)
         return s
 
-    def plane(fe):
-        p = rowdot(fe, 0)
-        for r in range(1, 7):
-            p = F32(p + rowdot(fe, r))
-        return p
+    def tree8(a):
+        a = [F32(v) for v in a]
+        return F32(F32(F32(a[0] + a[1]) + F32(a[2] + a[3])) + F32(F32(a[4] + a[5]) + F32(a[6] + a[7])))
 
-    total = None
-    for g in range(10):
-        grp = plane(7 * g)
-        for j in range(1, 7):
-            grp = F32(grp + plane(7 * g + j))
-        total = grp if total is None else F32(total + grp)
+    def plane(fe):
+        return tree8([rowdot(fe, r) for r in range(7)] + [0.0])
+
+    grp = [tree8([plane(7 * g + j) for j in range(7)] + [0.0]) for g in range(10)]
+    total = F32(tree8(grp[:8]) + F32(grp[8] + grp[9]))
     assert po.dense_dot(po.ORDER_FAST, f, w) == F32(total + plane(70))
 
 
