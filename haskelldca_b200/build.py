@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libdca_b200.so")
 SOURCES = ["dca_b200.cu"]
-DEPS = ["dca_b200.cu", "dca_kernels.cuh", "dca_state.h", os.path.join("..", "..", "include", "dca_b200.h")]
+DEPS = ["dca_b200.cu", "dca_kernels.cuh", "dca_fast.cuh", "dca_state.h", os.path.join("..", "..", "include", "dca_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "dca_kernels.cuh"
+#include "dca_fast.cuh"
 
 using namespace dca;
 
@@ -224,8 +225,8 @@ int launch_init(dca_handle* h, int only_replica) {
 bool bad_replica(const dca_handle* h, int r) { return !h || r < 0 || r >= h->n; }
 
 template <typename K>
-int set_smem(dca_handle* h, K kernel) {
-  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+int set_smem(dca_handle* h, K kernel, size_t bytes = sizeof(Smem)) {
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return DCA_OK;
 }
 
@@ -350,17 +351,12 @@ int dca_create(const dca_config* cfg, dca_handle** out) {
   h->tape_w.resize(h->n);
   h->tape_l.resize(h->n);
   h->tape_dirty = cfg->rng_mode == DCA_RNG_TAPE;
-  h->warps = cfg->warps_per_replica > 0 ? cfg->warps_per_replica : 4;
-  if (const char* e = getenv("DCA_WARPS")) {
-    int w = atoi(e);
-    if (w >= 1 && w <= 4) h->warps = w;
-  }
-  if (h->warps > 4) h->warps = 4;
-  if (cfg->order == DCA_ORDER_REF) h->warps = 4;  // 128 threads: one per candidate + V(s), x.wg
-  if ((rc = set_smem(h, k_run<ORDER_FAST, false>)) || (rc = set_smem(h, k_run<ORDER_FAST, true>)) ||
+  h->warps = 4;  // both kernels use 128-thread CTAs (warps_per_replica is accepted and ignored)
+  if ((rc = set_smem(h, fast::k_run_fast<false>, sizeof(fast::SmemF))) ||
+      (rc = set_smem(h, fast::k_run_fast<true>, sizeof(fast::SmemF))) ||
+      (rc = set_smem(h, fast::k_step_fast, sizeof(fast::SmemF))) ||
       (rc = set_smem(h, k_run<ORDER_REF, false>)) || (rc = set_smem(h, k_run<ORDER_REF, true>)) ||
-      (rc = set_smem(h, k_step<ORDER_FAST>)) || (rc = set_smem(h, k_step<ORDER_REF>)) ||
-      (rc = set_smem(h, k_gf_violates)))
+      (rc = set_smem(h, k_step<ORDER_REF>)) || (rc = set_smem(h, k_gf_violates)))
     return bail(rc);
   if ((rc = dca_reset(h))) return bail(rc);
   *out = h;
@@ -450,12 +446,12 @@ int dca_run(dca_handle* h, int64_t max_events) {
   a.trace = h->d_trace;
   a.trace_cap = h->cfg.trace_capacity;
   const bool trace = h->d_trace != nullptr;
-  const dim3 grid(h->n), block(32 * h->warps);
+  const dim3 grid(h->n), block(128);
   const size_t smem = sizeof(Smem);
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->cfg.order == DCA_ORDER_FAST) {
-    if (trace) k_run<ORDER_FAST, true><<<grid, block, smem, h->stream>>>(a);
-    else k_run<ORDER_FAST, false><<<grid, block, smem, h->stream>>>(a);
+    if (trace) fast::k_run_fast<true><<<grid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
+    else fast::k_run_fast<false><<<grid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
   } else {
     if (trace) k_run<ORDER_REF, true><<<grid, block, smem, h->stream>>>(a);
     else k_run<ORDER_REF, false><<<grid, block, smem, h->stream>>>(a);
@@ -487,7 +483,7 @@ static int step_launch(dca_handle* h, int replica, int mode, int r, int c, int i
   CK(cudaSetDevice(h->device));
   const int cell = r * COLS + c;
   if (h->cfg.order == DCA_ORDER_FAST)
-    k_step<ORDER_FAST><<<1, 128, sizeof(Smem), h->stream>>>(h->d_states, replica, mode, cell, is_end, ch, an, aa, ag, h->d_stepout);
+    fast::k_step_fast<<<1, fast::NT, sizeof(fast::SmemF), h->stream>>>(h->d_states, replica, mode, cell, is_end, ch, an, aa, ag, h->d_stepout);
   else
     k_step<ORDER_REF><<<1, 128, sizeof(Smem), h->stream>>>(h->d_states, replica, mode, cell, is_end, ch, an, aa, ag, h->d_stepout);
   h->launches++;

@@ -83,17 +83,6 @@ __device__ __forceinline__ float byte_f(uint32_t v, int i) {
   return (float)((v >> (8 * i)) & 0xFFu);
 }
 
-// rowdot of the FAST tree: s = x0*w0; s = fma(x_c, w_c, s), c = 1..6
-__device__ __forceinline__ float rowdot(uint2 xb, float4 wa, float4 wb) {
-  float s = __fmul_rn(byte_f(xb.x, 0), wa.x);
-  s = __fmaf_rn(byte_f(xb.x, 1), wa.y, s);
-  s = __fmaf_rn(byte_f(xb.x, 2), wa.z, s);
-  s = __fmaf_rn(byte_f(xb.x, 3), wa.w, s);
-  s = __fmaf_rn(byte_f(xb.y, 0), wb.x, s);
-  s = __fmaf_rn(byte_f(xb.y, 1), wb.y, s);
-  s = __fmaf_rn(byte_f(xb.y, 2), wb.z, s);
-  return s;
-}
 // tree8 over 8 consecutive lanes (xor butterfly); every lane gets the result
 __device__ __forceinline__ float tree8_lanes(float v) {
   v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -101,13 +90,6 @@ __device__ __forceinline__ float tree8_lanes(float v) {
   v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
   return v;
 }
-// tree8 of 8 values held by one thread
-__device__ __forceinline__ float tree8(float a0, float a1, float a2, float a3, float a4, float a5,
-                                       float a6, float a7) {
-  return __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3)),
-                   __fadd_rn(__fadd_rn(a4, a5), __fadd_rn(a6, a7)));
-}
-
 // ---------------------------------------------------------------------------
 // RNG: Philox4x32-10 (counter = draw index, stream id; key = seed) and the
 // operation-by-operation -log(u) of the Philox mode (DESIGN.md "Random numbers")
@@ -469,156 +451,6 @@ __device__ __forceinline__ void apply_action(Smem& sm, int cell, bool is_end, in
 }
 
 // ---------------------------------------------------------------------------
-// FAST order: plane/group sums and afterstate values by substitution
-// ---------------------------------------------------------------------------
-// planes and groups from the row sums R/G; returns val = x.w and dotg = x.wg. Warp 0.
-__device__ __forceinline__ void fast_planes(Smem& sm, float& val, float& dotg) {
-  Scratch& t = sm.t;
-  const int lane = lane_id();
-  for (int f = lane; f < NFEAT; f += 32) {
-    const float* r = &t.R[f * 7];
-    t.P[f] = tree8(r[0], r[1], r[2], r[3], r[4], r[5], r[6], 0.0f);
-    const float* g = &t.G[f * 7];
-    t.Pg[f] = tree8(g[0], g[1], g[2], g[3], g[4], g[5], g[6], 0.0f);
-  }
-  __syncwarp();
-  // lanes 0..9: w groups; lanes 16..25: wg groups
-  float grp = 0.0f;
-  {
-    int g = lane & 15;
-    const float* p = (lane < 16) ? &t.P[7 * g] : &t.Pg[7 * g];
-    if (g < 10) grp = tree8(p[0], p[1], p[2], p[3], p[4], p[5], p[6], 0.0f);
-    if (lane < 10) t.Gs[lane] = grp;
-  }
-  // totals: (tree8(G0..7) + (G8 + G9)) + plane70, for w (lanes 0..15) and wg (16..31)
-  float t8 = tree8_lanes(grp);  // lanes 0-7 / 16-23 hold tree8(G0..G7)
-  float g8 = __shfl_sync(0xffffffffu, grp, (lane & 16) + 8);
-  float g9 = __shfl_sync(0xffffffffu, grp, (lane & 16) + 9);
-  float tot = __fadd_rn(__fadd_rn(t8, __fadd_rn(g8, g9)), (lane < 16) ? t.P[70] : t.Pg[70]);
-  val = __shfl_sync(0xffffffffu, tot, 0);
-  dotg = __shfl_sync(0xffffffffu, tot, 16);
-  __syncwarp();
-}
-
-// q[k] = dense dot of afterstate k in the FAST tree, computed by substituting the
-// two planes the action touches (channel plane ch, n_elig plane 70).  Warp 0;
-// 4 candidates per pass, 8 lanes (7 rows + pad) per candidate.
-__device__ __forceinline__ void fast_qeval(Smem& sm, int n, bool is_end) {
-  RepState& s = sm.s;
-  Scratch& t = sm.t;
-  const int lane = lane_id(), r = lane & 7, seg = lane >> 3;
-  const bool rv = r < 7;
-  const int rr = rv ? r : 0;
-  const uint32_t want = is_end ? 1u : 0u;
-  // event-constant pieces of this lane's row
-  const uint2 x70 = *reinterpret_cast<const uint2*>(&s.x[NCH * PLANE + rr * ROWPAD]);
-  const float4 w70a = *reinterpret_cast<const float4*>(&s.w[NCH * PLANE + rr * ROWPAD]);
-  const float4 w70b = *reinterpret_cast<const float4*>(&s.w[NCH * PLANE + rr * ROWPAD + 4]);
-  const uint2 n4 = t.n4b[rr], n2 = t.n2b[rr];
-  const float gs_r = t.Gs[r];  // group sums 0..7 for the top-level tree
-  const float gs8 = t.Gs[8], gs9 = t.Gs[9];
-  for (int base = 0; base < n; base += 4) {
-    const int k = base + seg;
-    const bool valid = k < n;
-    const int ch = t.cand[valid ? k : n - 1];
-    // channel plane: x' = x +- [cell in N4]
-    uint2 xr = *reinterpret_cast<const uint2*>(&s.x[ch * PLANE + rr * ROWPAD]);
-    if (is_end) { xr.x -= n4.x; xr.y -= n4.y; } else { xr.x += n4.x; xr.y += n4.y; }
-    const float4 wa = *reinterpret_cast<const float4*>(&s.w[ch * PLANE + rr * ROWPAD]);
-    const float4 wb = *reinterpret_cast<const float4*>(&s.w[ch * PLANE + rr * ROWPAD + 4]);
-    float rowP = rv ? rowdot(xr, wa, wb) : 0.0f;
-    // n_elig plane: e' = e -+ [cell in N2 and ch eligible there on grid']
-    const uint2 cr = *reinterpret_cast<const uint2*>(&s.cnt2[ch * PLANE + rr * ROWPAD]);
-    uint2 er = x70;
-    const uint32_t c0 = n2.x & eq_bytes(cr.x, want), c1 = n2.y & eq_bytes(cr.y, want);
-    if (is_end) { er.x += c0; er.y += c1; } else { er.x -= c0; er.y -= c1; }
-    float rowE = rv ? rowdot(er, w70a, w70b) : 0.0f;
-    const float Pp = tree8_lanes(rowP);
-    const float Ep = tree8_lanes(rowE);
-    // group of ch with plane ch substituted
-    const int gi = ch / 7, ji = ch - 7 * gi;
-    float v = rv ? ((r == ji) ? Pp : t.P[7 * gi + r]) : 0.0f;
-    const float Gp = tree8_lanes(v);
-    // top level with group gi substituted
-    float u = (r == gi) ? Gp : gs_r;
-    const float T8 = tree8_lanes(u);
-    const float g8 = (gi == 8) ? Gp : gs8, g9 = (gi == 9) ? Gp : gs9;
-    const float qv = __fadd_rn(__fadd_rn(T8, __fadd_rn(g8, g9)), Ep);
-    if (r == 0 && valid) t.q[k] = qv;
-  }
-  __syncwarp();
-}
-
-// Row sums R (x.w) and G (x.wg) of the current state; all threads.
-__device__ __forceinline__ void fast_rowsums(Smem& sm) {
-  RepState& s = sm.s;
-  for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
-    const int off = (row / 7) * PLANE + (row % 7) * ROWPAD;
-    const uint2 xb = *reinterpret_cast<const uint2*>(&s.x[off]);
-    const float4 wa = *reinterpret_cast<const float4*>(&s.w[off]);
-    const float4 wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
-    const float4 ga = *reinterpret_cast<const float4*>(&s.wg[off]);
-    const float4 gb = *reinterpret_cast<const float4*>(&s.wg[off + 4]);
-    sm.t.R[row] = rowdot(xb, wa, wb);
-    sm.t.G[row] = rowdot(xb, ga, gb);
-  }
-}
-
-// Dense TDC update (Agent.hs:67-76) fused with the next event's row sums.
-// s.x already holds x' (the afterstate); the pre-action x is rebuilt for the two
-// planes the action touched.  FAST arithmetic:
-//   g = fma(-cdot, x', fma(ctd, x, cavg));  w' = w - g;  wg' = fma(sg, x, wg)
-__device__ __forceinline__ void fast_dense_update(Smem& sm) {
-  RepState& s = sm.s;
-  Scratch& t = sm.t;
-  const float ctd = t.ctd, cavg = t.cavg, ncdot = -t.cdot, sg = t.sg;
-  const int act_ch = t.act_ch, diff = t.act_diff;
-  for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
-    const int f = row / 7, r = row - 7 * f;
-    const int off = f * PLANE + r * ROWPAD;
-    const uint2 xn = *reinterpret_cast<const uint2*>(&s.x[off]);
-    uint2 xo = xn;
-    if (act_ch >= 0) {
-      if (f == act_ch) {
-        uint2 d = t.n4b[r];
-        if (diff > 0) { xo.x -= d.x; xo.y -= d.y; } else { xo.x += d.x; xo.y += d.y; }
-      } else if (f == NCH) {
-        uint2 d = t.chgb[r];
-        if (diff > 0) { xo.x += d.x; xo.y += d.y; } else { xo.x -= d.x; xo.y -= d.y; }
-      }
-    }
-    float4 wa = *reinterpret_cast<const float4*>(&s.w[off]);
-    float4 wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
-    float4 ga = *reinterpret_cast<const float4*>(&s.wg[off]);
-    float4 gb = *reinterpret_cast<const float4*>(&s.wg[off + 4]);
-    float rs, rg;
-#define DCA_UPD(WV, GV, XN, XO, FIRST)                                   \
-  {                                                                      \
-    const float xnf = (XN), xof = (XO);                                  \
-    const float g_ = __fmaf_rn(ncdot, xnf, __fmaf_rn(ctd, xof, cavg));   \
-    WV = __fsub_rn(WV, g_);                                              \
-    GV = __fmaf_rn(sg, xof, GV);                                         \
-    if (FIRST) { rs = __fmul_rn(xnf, WV); rg = __fmul_rn(xnf, GV); }     \
-    else { rs = __fmaf_rn(xnf, WV, rs); rg = __fmaf_rn(xnf, GV, rg); }   \
-  }
-    DCA_UPD(wa.x, ga.x, byte_f(xn.x, 0), byte_f(xo.x, 0), true)
-    DCA_UPD(wa.y, ga.y, byte_f(xn.x, 1), byte_f(xo.x, 1), false)
-    DCA_UPD(wa.z, ga.z, byte_f(xn.x, 2), byte_f(xo.x, 2), false)
-    DCA_UPD(wa.w, ga.w, byte_f(xn.x, 3), byte_f(xo.x, 3), false)
-    DCA_UPD(wb.x, gb.x, byte_f(xn.y, 0), byte_f(xo.y, 0), false)
-    DCA_UPD(wb.y, gb.y, byte_f(xn.y, 1), byte_f(xo.y, 1), false)
-    DCA_UPD(wb.z, gb.z, byte_f(xn.y, 2), byte_f(xo.y, 2), false)
-#undef DCA_UPD
-    *reinterpret_cast<float4*>(&s.w[off]) = wa;
-    *reinterpret_cast<float4*>(&s.w[off + 4]) = wb;
-    *reinterpret_cast<float4*>(&s.wg[off]) = ga;
-    *reinterpret_cast<float4*>(&s.wg[off + 4]) = gb;
-    t.R[row] = rs;
-    t.G[row] = rg;
-  }
-}
-
-// ---------------------------------------------------------------------------
 // REF order: reference-literal arithmetic (Accelerate Interpreter)
 // ---------------------------------------------------------------------------
 // dense right fold over flatten order i = cell*71 + f, i = 3478..0, of
@@ -787,7 +619,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     }
     __syncwarp();
   }
-  if (ORDER == ORDER_REF) {
+  {
     __syncthreads();
     const int n = t.ncand;
     const bool is_end = t.ev_is_end;
@@ -801,14 +633,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
   if (wid == 0) {
     const int n = t.ncand, cell = t.ev_cell;
     const bool is_end = t.ev_is_end;
-    float val, dotg;
-    if (ORDER == ORDER_FAST) {
-      fast_planes(sm, val, dotg);
-      if (n > 0) fast_qeval(sm, n, is_end);
-    } else {
-      val = t.val;
-      dotg = t.dotg;
-    }
+    const float val = t.val, dotg = t.dotg;
     int act = -1;
     float next_val = val;  // no action: nextFrep = frep (Simulator.hs:170-171)
     if (n > 0) {
@@ -847,8 +672,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
   }
   __syncthreads();
   // ---- accFn2's dense part: weight / gradient-correction update ----
-  if (ORDER == ORDER_FAST) fast_dense_update(sm);
-  else ref_dense_update(sm);
+  ref_dense_update(sm);
   if (TRACE) state_hashes(sm);
   __syncthreads();
   if (wid == 0) {
@@ -898,10 +722,6 @@ __global__ void __launch_bounds__(128) k_run(RunArgs a) {
   stage_in(sm, g);
   __syncthreads();
   if (!sm.s.initialized || sm.s.status != ST_RUNNING) return;  // uniform
-  if (ORDER == ORDER_FAST) {
-    fast_rowsums(sm);
-    __syncthreads();
-  }
   QRegs q{sm.s.n_end, sm.s.next_id};
   Rng rng = make_rng(a, sm.s, rep);
   for (long long it = 0; it < a.max_events; ++it) {
@@ -1063,10 +883,6 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   const int wid = warp_id(), lane = lane_id(), nthreads = blockDim.x;
   stage_in(sm, states + rep);
   __syncthreads();
-  if (ORDER == ORDER_FAST) {
-    fast_rowsums(sm);
-    __syncthreads();
-  }
   if (wid == 0) {
     const int n = build_candidates(sm, cell, is_end);
     if (lane == 0) {
@@ -1079,7 +895,7 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   }
   __syncthreads();
   const int n = t.ncand;
-  if (ORDER == ORDER_REF) {
+  {
     for (int k = threadIdx.x; k < n; k += nthreads - 2)
       if (threadIdx.x < nthreads - 2) t.q[k] = ref_dense_dot(sm, s.w, t.cand[k], is_end);
     if (threadIdx.x == nthreads - 1) t.val = ref_dense_dot(sm, s.w, -1, false);
@@ -1087,14 +903,7 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
     __syncthreads();
   }
   if (wid == 0) {
-    float val, dotg;
-    if (ORDER == ORDER_FAST) {
-      fast_planes(sm, val, dotg);
-      if (n > 0) fast_qeval(sm, n, is_end);
-    } else {
-      val = t.val;
-      dotg = t.dotg;
-    }
+    const float val = t.val, dotg = t.dotg;
     int act = -1;
     float next_val = val;
     if (n > 0) {
@@ -1131,8 +940,7 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   }
   __syncthreads();
   if (mode == 1) {
-    if (ORDER == ORDER_FAST) fast_dense_update(sm);
-    else ref_dense_update(sm);
+    ref_dense_update(sm);
     __syncthreads();
     stage_out(sm, states + rep);
   }

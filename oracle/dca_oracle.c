@@ -325,20 +325,35 @@ static float dot_ref(const int64_t *x, const float *w) {
   return acc;
 }
 
-/* FAST canonical tree (see header). Flatten index i = (r*7+c)*71 + f.
- *   rowdot(f,r) = fma chain over the 7 columns (first term a plain product)
- *   tree8(a0..a7) = ((a0+a1)+(a2+a3)) + ((a4+a5)+(a6+a7))
- *   plane(f)  = tree8(rowdot(f,0..6), 0)
- *   group(g)  = tree8(plane(7g..7g+6), 0),  g = 0..9
- *   dot       = (tree8(group(0..7)) + (group(8)+group(9))) + plane(70)
- * (an xor-butterfly over 8 lanes computes tree8 in 3 shuffle steps). */
+/* FAST canonical trees (see header). Flatten index i = (r*7+c)*71 + f.  The
+ * shapes follow the thread layout of the sm_100a kernel (96 "agent" threads =
+ * 12 groups of 8 lanes; lane r of a group owns row r of one feature plane per
+ * slot, plane f = 12*slot + group), so that every partial sum is either
+ * thread-local or one xor-shuffle away:
+ *   rowdot(f,r) = e + o with two fma chains over the even / odd columns
+ *                 (what one f32x2 accumulator pair computes):
+ *                 e = x0*w0; e = fma(x2,w2,e); e = fma(x4,w4,e); e = fma(x6,w6,e)
+ *                 o = x1*w1; o = fma(x3,w3,o); o = fma(x5,w5,o)
+ *   plane(f)    = bfly8(rowdot(f,0..6), 0)        -- xor-butterfly 1,2,4 =
+ *                 ((a0+a1)+(a2+a3)) + ((a4+a5)+(a6+a7))
+ *   x.w   (V):  v[l] = (plane(l) + plane(l+32)) + (l < 6 ? plane(l+64) : 0), l = 0..31
+ *               xor-butterfly 1,2,4,8,16 over v[0..31], then + plane(70)
+ *   x.wg:       thread (group g, row r): s = rowdot(g,r); s += rowdot(12j+g, r),
+ *               j = 1..5 while 12j+g <= 70; row 7 = 0;  warp sums by
+ *               xor-butterfly 1..16 over the 32 lanes (4 groups) of each of the
+ *               3 warps; total = (W0 + W1) + W2. */
 static float tree8(const float a[8]) {
   return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 static float rowdot_fast(const int64_t *x, const float *w, int f, int r) {
-  float s = (float)x[FIDX(r, 0, f)] * w[FIDX(r, 0, f)];
-  for (int c = 1; c < C_; ++c) s = fmaf((float)x[FIDX(r, c, f)], w[FIDX(r, c, f)], s);
-  return s;
+  float e = (float)x[FIDX(r, 0, f)] * w[FIDX(r, 0, f)];
+  float o = (float)x[FIDX(r, 1, f)] * w[FIDX(r, 1, f)];
+  e = fmaf((float)x[FIDX(r, 2, f)], w[FIDX(r, 2, f)], e);
+  o = fmaf((float)x[FIDX(r, 3, f)], w[FIDX(r, 3, f)], o);
+  e = fmaf((float)x[FIDX(r, 4, f)], w[FIDX(r, 4, f)], e);
+  o = fmaf((float)x[FIDX(r, 5, f)], w[FIDX(r, 5, f)], o);
+  e = fmaf((float)x[FIDX(r, 6, f)], w[FIDX(r, 6, f)], e);
+  return e + o;
 }
 static float plane_fast(const int64_t *x, const float *w, int f) {
   float a[8];
@@ -346,19 +361,47 @@ static float plane_fast(const int64_t *x, const float *w, int f) {
   a[7] = 0.0f;
   return tree8(a);
 }
-static float dot_fast(const int64_t *x, const float *w) {
-  float grp[10];
-  for (int g = 0; g < 10; ++g) {
-    float a[8];
-    for (int j = 0; j < 7; ++j) a[j] = plane_fast(x, w, 7 * g + j);
-    a[7] = 0.0f;
-    grp[g] = tree8(a);
+static void bfly32(float v[32]) { /* xor-butterfly 1,2,4,8,16: every lane ends with the same sum */
+  for (int s = 1; s < 32; s <<= 1) {
+    float t[32];
+    for (int l = 0; l < 32; ++l) t[l] = v[l] + v[l ^ s];
+    memcpy(v, t, sizeof t);
   }
-  return (tree8(grp) + (grp[8] + grp[9])) + plane_fast(x, w, CH_);
+}
+static float dot_fast(const int64_t *x, const float *w) {
+  float v[32];
+  for (int l = 0; l < 32; ++l) {
+    float p2 = (l < 6) ? plane_fast(x, w, l + 64) : 0.0f;
+    v[l] = (plane_fast(x, w, l) + plane_fast(x, w, l + 32)) + p2;
+  }
+  bfly32(v);
+  return v[0] + plane_fast(x, w, CH_);
+}
+static float dot_fast_g(const int64_t *x, const float *wg) {
+  float W[3];
+  for (int wp = 0; wp < 3; ++wp) {
+    float v[32];
+    for (int l = 0; l < 32; ++l) {
+      const int g = 4 * wp + (l >> 3), r = l & 7;
+      float s = 0.0f;
+      if (r < R_) {
+        s = rowdot_fast(x, wg, g, r);
+        for (int j = 1; j < 6 && 12 * j + g <= CH_; ++j) s = s + rowdot_fast(x, wg, 12 * j + g, r);
+      }
+      v[l] = s;
+    }
+    bfly32(v);
+    W[wp] = v[0];
+  }
+  return (W[0] + W[1]) + W[2];
 }
 
 float orc_dense_dot(int order, const int64_t *frep, const float *w) {
   return order == ORC_ORDER_FAST ? dot_fast(frep, w) : dot_ref(frep, w);
+}
+/* x . wGradCorr (Agent.hs:66): same right fold in REF, its own tree in FAST */
+float orc_dense_dot_g(int order, const int64_t *frep, const float *wg) {
+  return order == ORC_ORDER_FAST ? dot_fast_g(frep, wg) : dot_ref(frep, wg);
 }
 
 float orc_forward(int order, const int64_t *frep, const float *w) { /* Agent.hs:15-23 */
@@ -416,7 +459,7 @@ float orc_backward(int order, float aN, float aA, float aG, const int64_t *frep,
   const float val = orc_dense_dot(order, frep, w);           /* :62 */
   const float next_val = orc_dense_dot(order, next_frep, w); /* :63 */
   const float td = ((reward - avgR) + next_val) - val;       /* :65 */
-  const float dot = orc_dense_dot(order, frep, wg);          /* :66 */
+  const float dot = orc_dense_dot_g(order, frep, wg);        /* :66 */
   const float c = -2.0f * aN;                                /* :67 */
   const float ctd = c * td, cavg = c * avgR, cdot = c * dot;
   const float s = aG * (td - dot); /* :75 */

@@ -25,11 +25,12 @@
  *                    afterstate GEMV, each dot a sequential RIGHT fold
  *                    x0+(x1+(...+(x_{n-1}+0))) in flatten order, products and
  *                    sums rounded separately, no FMA.
- *   ORC_ORDER_FAST : the same dense dots re-associated into a fixed tree
- *                    (7-col row chains with FMA -> tree8 over the 7 rows of a
- *                    feature plane -> tree8 over groups of 7 channel planes ->
- *                    total + n_elig plane; see dot_fast) and the TDC
- *                    update written with explicit FMAs.  Accelerate's `fold`
+ *   ORC_ORDER_FAST : the same dense dots re-associated into fixed trees that
+ *                    follow the thread layout of the sm_100a kernel (even/odd
+ *                    fma chains over the 7 columns of a row -> xor-butterfly
+ *                    over the rows of a feature plane -> butterfly over the
+ *                    planes; see dot_fast / dot_fast_g) and the TDC update
+ *                    written with explicit FMAs.  Accelerate's `fold`
  *                    requires an associative operator and leaves the order
  *                    unspecified, so this is a legal execution of the same
  *                    program; it is the order the throughput kernel uses.
@@ -131,6 +132,7 @@ int64_t orc_bool_sum(const uint8_t *grid);                                   /* 
 
 /* ---- agent: src/Agent.hs, src/AccUtils.hs:203-228, src/Simulator.hs:137-205 ---- */
 float orc_dense_dot(int order, const int64_t *frep, const float *w);         /* vvMul / mvMul row */
+float orc_dense_dot_g(int order, const int64_t *frep, const float *wg);      /* vvMul x wGradCorr, Agent.hs:66 */
 float orc_forward(int order, const int64_t *frep, const float *w);           /* Agent.hs:22-23 */
 int orc_argpmax(const float *q, int n);                                      /* last max wins */
 /* selectAction: returns idx (into chs), writes qval and the chosen afterstate frep */

@@ -116,6 +116,7 @@ def lib():
             "orc_inc_afterstate_freps": (None, [i32, i32, i32, vp, i32, vp, vp, vp]),
             "orc_bool_sum": (i64, [vp]),
             "orc_dense_dot": (f32, [i32, vp, vp]),
+            "orc_dense_dot_g": (f32, [i32, vp, vp]),
             "orc_forward": (f32, [i32, vp, vp]),
             "orc_argpmax": (i32, [vp, i32]),
             "orc_select_action": (i32, [i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
@@ -289,6 +290,11 @@ def bool_sum(grid) -> int:
 # ---- agent -----------------------------------------------------------------
 def dense_dot(order, frep, w) -> np.float32:
     return np.float32(lib().orc_dense_dot(order, _p(_frep(frep)), _p(_f32(w))))
+
+
+def dense_dot_g(order, frep, wg) -> np.float32:
+    """x . wGradCorr (Agent.hs:66): the FAST order uses its own (thread-mapped) tree for this dot."""
+    return np.float32(lib().orc_dense_dot_g(order, _p(_frep(frep)), _p(_f32(wg))))
 
 
 def argpmax(q) -> int:

@@ -35,30 +35,66 @@ def test_dense_dot_ref_is_a_right_fold():  # Interpreter fold: x0+(x1+(...+(xn-1
     assert po.dense_dot(po.ORDER_REF, f, w) == acc
 
 
-def test_dense_dot_fast_tree():
-    _, f, w, _ = _state(2)
+def _fast_pieces(f, w):
+    """numpy restatement of the FAST trees (oracle/dca_oracle.c dot_fast / dot_fast_g)."""
     x = f.astype(np.float64)
     w3 = w.reshape(7, 7, 71)
 
     def fma(a, b, c):  # exact in float64 then one rounding: |a|<=70, 24-bit b -> product exact
         return F32(np.float64(a) * np.float64(b) + np.float64(c))
 
-    def rowdot(fe, r):
-        s = F32(F32(x[r, 0, fe]) * w3[r, 0, fe])
-        for c in range(1, 7):
-            s = fma(x[r, c, fe], w3[r, c, fe], s)
-        return s
+    def rowdot(fe, r):  # even / odd column chains = one f32x2 accumulator pair
+        e = F32(F32(x[r, 0, fe]) * w3[r, 0, fe])
+        o = F32(F32(x[r, 1, fe]) * w3[r, 1, fe])
+        e = fma(x[r, 2, fe], w3[r, 2, fe], e)
+        o = fma(x[r, 3, fe], w3[r, 3, fe], o)
+        e = fma(x[r, 4, fe], w3[r, 4, fe], e)
+        o = fma(x[r, 5, fe], w3[r, 5, fe], o)
+        e = fma(x[r, 6, fe], w3[r, 6, fe], e)
+        return F32(e + o)
 
-    def tree8(a):
-        a = [F32(v) for v in a]
-        return F32(F32(F32(a[0] + a[1]) + F32(a[2] + a[3])) + F32(F32(a[4] + a[5]) + F32(a[6] + a[7])))
+    def bfly(v):  # xor-butterfly over len(v) lanes
+        v = [F32(a) for a in v]
+        s = 1
+        while s < len(v):
+            v = [F32(v[l] + v[l ^ s]) for l in range(len(v))]
+            s <<= 1
+        assert all(a == v[0] or (np.isnan(a) and np.isnan(v[0])) for a in v)
+        return v[0]
 
     def plane(fe):
-        return tree8([rowdot(fe, r) for r in range(7)] + [0.0])
+        return bfly([rowdot(fe, r) for r in range(7)] + [F32(0.0)])
 
-    grp = [tree8([plane(7 * g + j) for j in range(7)] + [0.0]) for g in range(10)]
-    total = F32(tree8(grp[:8]) + F32(grp[8] + grp[9]))
-    assert po.dense_dot(po.ORDER_FAST, f, w) == F32(total + plane(70))
+    return rowdot, bfly, plane
+
+
+def test_dense_dot_fast_tree():
+    _, f, w, _ = _state(2)
+    rowdot, bfly, plane = _fast_pieces(f, w)
+    v = [F32(F32(plane(l) + plane(l + 32)) + (plane(l + 64) if l < 6 else F32(0.0))) for l in range(32)]
+    assert po.dense_dot(po.ORDER_FAST, f, w) == F32(bfly(v) + plane(70))
+
+
+def test_dense_dot_g_fast_tree():  # x . wGradCorr: per-thread slot sums, warp butterflies, (W0 + W1) + W2
+    _, f, _, wg = _state(2)
+    wg = (wg + np.linspace(-1, 1, wg.size, dtype=F32)).astype(F32)
+    rowdot, bfly, _ = _fast_pieces(f, wg)
+    W = []
+    for wp in range(3):
+        v = []
+        for lane in range(32):
+            g, r = 4 * wp + lane // 8, lane % 8
+            s = F32(0.0)
+            if r < 7:
+                s = rowdot(g, r)
+                j = 1
+                while j < 6 and 12 * j + g <= 70:
+                    s = F32(s + rowdot(12 * j + g, r))
+                    j += 1
+            v.append(s)
+        W.append(bfly(v))
+    assert po.dense_dot_g(po.ORDER_FAST, f, wg) == F32(F32(W[0] + W[1]) + W[2])
+    assert po.dense_dot_g(po.ORDER_REF, f, wg) == po.dense_dot(po.ORDER_REF, f, wg)
 
 
 @pytest.mark.parametrize("order", [po.ORDER_REF, po.ORDER_FAST])
@@ -69,7 +105,7 @@ def test_backward_matches_numpy_restatement(order):  # Agent.hs:44-81
     nf = po.inc_afterstate_freps(cell, False, chs, g, f)[0]
     aN, aA, aG, avgR, reward = F32(2.52e-6), F32(0.06), F32(5e-6), F32(123.5), F32(151)
     loss, isnan, w2, wg2, avg2 = po.backward(order, aN, aA, aG, f, nf, reward, w, wg, avgR)
-    val, nval, dot = po.dense_dot(order, f, w), po.dense_dot(order, nf, w), po.dense_dot(order, f, wg)
+    val, nval, dot = po.dense_dot(order, f, w), po.dense_dot(order, nf, w), po.dense_dot_g(order, f, wg)
     td = F32(F32(F32(reward - avgR) + nval) - val)
     assert loss == td and not isnan
     c = F32(F32(-2.0) * aN)
