@@ -116,7 +116,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB
+    """The product library; DCA_LIB selects a development variant built with build.build(out=...)."""
+    return os.environ.get("DCA_LIB") or _build.LIB
 
 
 def load(build_if_missing: bool = True):
@@ -125,7 +126,7 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if build_if_missing and _build.is_stale():
+    if build_if_missing and path == _build.LIB and _build.is_stale():
         _build.build()
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: build it with `python -m haskelldca_b200.build` (nvcc, sm_100a)")

@@ -34,11 +34,13 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """`extra_flags` / `out` build a development variant (e.g. -DDCA_MIN_CTAS=4) next to the product library."""
+    out = out or LIB
+    if not force and out == LIB and not is_stale():
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra_flags, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -46,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     env.pop("CC", None)  # the image's CC wrapper is not a valid nvcc host compiler
     env.pop("CXX", None)
     subprocess.check_call(cmd, cwd=CSRC, env=env)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -6,22 +6,23 @@
 //              feature plane f = 12*slot + g for slot = 0..5.  wGradCorr lives in
 //              those threads' registers (6 x 7 floats), wNet in shared memory (the
 //              afterstate evaluation needs it with a flexible lane mapping).
-//   warp 3     "event" warp: event queue, random numbers, statistics, candidate
-//              channels, stop rules (environmentStep, src/Simulator.hs:101-134).
+//   warp 3     "event" warp: event queue, random numbers, statistics, grid bits,
+//              candidate channels, stop rules (environmentStep, src/Simulator.hs:101-134).
 //
-// Per event (runStep, src/SimRunner.hs:60-97) -- three CTA barriers:
-//   [Q]   V(s) = x.w from the plane sums (butterfly), then every candidate channel
-//         on its own 8-lane group: the two planes the action touches are
+// Per event (runStep, src/SimRunner.hs:60-97) -- two CTA barriers:
+//   B1 -> agents: V(s) = x.w from the plane sums (butterfly), then every candidate
+//         channel on its own 8-lane group: the two planes the action touches are
 //         re-evaluated and substituted into the V tree (selectAction,
-//         src/Simulator.hs:185-205 with incAfterStateFreps, src/Gridfuncs.hs:186-252)
-//   B2    argmax (last maximum wins, src/AccUtils.hs:203-208), TD scalars
-//         (src/Agent.hs:62-78) replicated in every thread; warp 0 executes the
-//         action on grid / frep / cnt2 (src/Gridfuncs.hs:105-110); the event warp
-//         books the statistics, pushes the new events and pops the next one
-//   B3    agent warps: dense w / wGradCorr update fused with the next event's row
-//         sums (src/Agent.hs:67-76);  event warp, concurrently: candidate channels
-//         of the next event, queue pre-scan, random draws, stop rules
-//   B1
+//         src/Simulator.hs:185-205 with incAfterStateFreps, src/Gridfuncs.hs:186-252).
+//         event warp: V(s), queue pre-scan, random draws.
+//   B2 -> every thread: argmax (last maximum wins, src/AccUtils.hs:203-208) and the
+//         TD scalars (src/Agent.hs:62-78), replicated.
+//         agents: dense w / wGradCorr update (src/Agent.hs:67-76) fused with moving
+//         frep / cnt2 to the chosen afterstate (the owners of the touched rows do it)
+//         and with the next event's row sums.
+//         event warp, concurrently: grid bit (src/Gridfuncs.hs:105-110), statistics,
+//         new events, the next event and its candidate channels, stop rules.
+//   -> B1
 //
 // The fp32 arithmetic is the FAST order specified in DESIGN.md ("Arithmetic
 // orders"; the CPU checker restates it independently): every operation is an explicit
@@ -40,13 +41,16 @@ constexpr int NSLOT = 6;      // feature planes per agent lane group
 constexpr int SLOTP = 12;     // planes per slot = agent lane groups
 constexpr int WH = NROW * 4;  // floats per half of the weight array
 
-struct Ev {  // the event being processed and its candidate set
+struct Ev {  // an event and its candidate set (double-buffered: the event warp writes
+             // the next one while the agents still use the current one)
   double time;
   int type, cell, ch, hoff;
   int ncand, pad;
+  uint2 n4b[8], n2b[8];  // row byte masks of the event cell: N4 \ {cell}, N2 u {cell}
+  uint8_t cand[72];      // candidate channels, ascending
 };
 
-struct SmemF {
+struct alignas(16) SmemF {
   float w[2][WH];           // wNet: columns 0-3 of row rho = f*7+r at [0][rho*4+c], columns 4-6 at [1][rho*4+c-4]
   uint8_t x[WPAD];          // frep, [f][r][8]
   uint8_t cnt2[WPAD];       // users of ch within distance 2, [ch][r][8]
@@ -56,20 +60,18 @@ struct SmemF {
   uint16_t q_key[QCAP];
   uint8_t q_hoff[QCAP];
   long long stats[8];
+  Ev ev[2];
   float P[72];              // plane sums of x.w (current state, current weights)
   float q[72];              // afterstate values of the candidates
   float Wg[4];              // per-warp partial sums of x.wGradCorr
-  uint2 n4b[8], n2b[8];     // row byte masks of the event cell: N4 \ {cell}, N2 u {cell}
-  uint2 chgb[8];            // cells whose n_elig changes under the chosen action
-  unsigned long long chgmask, n4mask, n2mask;
-  Ev ev;
-  int status, pad0;
-  uint8_t cand[72];
+  int status, pad0, pad1, pad2;
 };
 static_assert(sizeof(SmemF) % 16 == 0, "SmemF size");
 static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && offsetof(SmemF, grid) % 16 == 0 &&
               offsetof(SmemF, q_time) % 16 == 0 && offsetof(SmemF, q_id) % 16 == 0 && offsetof(SmemF, q_key) % 16 == 0 &&
-              offsetof(SmemF, q_hoff) % 8 == 0 && offsetof(SmemF, n4b) % 8 == 0, "SmemF alignment");
+              offsetof(SmemF, q_hoff) % 8 == 0 && offsetof(SmemF, ev) % 8 == 0 && sizeof(Ev) % 8 == 0, "SmemF alignment");
+
+__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------
 // packed fp32 helpers
@@ -121,39 +123,82 @@ struct TdScalars {
   float ctd, cavg, ncdot, sg;
 };
 
-// The dense pass over this lane's rows.  UPDATE: w' = w - g, wg' = fma(sg, x, wg)
-// (Agent.hs:67-76) with x = the pre-action features, rebuilt for the two planes
-// the action touched; then the row sums of x'.w' -> plane sums P, and the lane's
-// partial of x'.wg' -> warp sums Wg.  Without UPDATE only the sums are formed.
+// Per-thread constants of an agent lane: where its rows live.
+struct Lane {
+  int g8, r;          // lane group (0..11), row (0..7; 7 idles)
+  int xoff, xoff5;    // byte offset of this lane's row in sm.x for slots 0-4 (+672*j) / slot 5
+  int woff, woff5;    // float offset of this lane's row in a half of sm.w (+336*j) / slot 5
+  bool rv, pv5;       // row valid; plane of slot 5 valid
+};
+__device__ __forceinline__ Lane make_lane() {
+  Lane l;
+  l.g8 = threadIdx.x >> 3;
+  l.r = threadIdx.x & 7;
+  l.rv = l.r < 7;
+  const int rc = l.rv ? l.r : 6;
+  l.pv5 = SLOTP * (NSLOT - 1) + l.g8 <= NCH;
+  const int f5 = l.pv5 ? SLOTP * (NSLOT - 1) + l.g8 : NCH;
+  l.xoff = l.g8 * PLANE + rc * ROWPAD;
+  l.xoff5 = f5 * PLANE + rc * ROWPAD;
+  l.woff = (l.g8 * 7 + rc) * 4;
+  l.woff5 = (f5 * 7 + rc) * 4;
+  return l;
+}
+
+// The dense pass over this lane's rows (one row of one plane per slot).
+// UPDATE: sm.x holds the PRE-action features x.  The owners of the rows the
+// action touches move them to the afterstate x' (plane `act`: +-1 on N4 \ {cell},
+// Gridfuncs.hs:212-217; plane 70 and cnt2[act]: Gridfuncs.hs:220-252), then
+//   g = fma(-cdot, x', fma(ctd, x, cavg));  w' = w - g;  wg' = fma(sg, x, wg)   (Agent.hs:67-76)
+// and the row sums of x'.w' -> plane sums P, x'.wg' -> warp sums Wg (for the next event).
+// Without UPDATE only the sums of the current state are formed.
 template <bool UPDATE>
-__device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const int g8, const int r, const int act,
-                                           const bool is_end, const TdScalars td, const uint2 n4b_r) {
-  const int rc = r < 7 ? r : 6;
-  const bool rv = r < 7;
+__device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, const int act, const bool is_end,
+                                           const TdScalars td, const uint2 n4b_r, const uint2 n2b_r) {
+  const int wid = warp_id();
+  // this lane's row of the N4 mask as floats; x' = x + sgn * mask on plane `act`
+  Row7 dn4;
+  const float sgn = is_end ? -1.0f : 1.0f;
+  if (UPDATE) dn4 = cvt_row(n4b_r);
+  float rs[NSLOT];
   float rg_acc = 0.0f;
-  uint2 chgb_r = make_uint2(0, 0);
-  if (UPDATE) chgb_r = sm.chgb[rc];
 #pragma unroll
   for (int j = 0; j < NSLOT; ++j) {
-    int f = SLOTP * j + g8;
-    const bool pv = (j < NSLOT - 1) || (f <= NCH);
-    if (j == NSLOT - 1 && f > NCH) f = NCH;
-    const bool valid = pv && rv;
-    const int row = f * 7 + rc;
-    const uint2 xb = *reinterpret_cast<const uint2*>(&sm.x[f * PLANE + rc * ROWPAD]);
-    float4 wa = *reinterpret_cast<const float4*>(&sm.w[0][row * 4]);
-    float4 wb = *reinterpret_cast<const float4*>(&sm.w[1][row * 4]);
+    const bool last = j == NSLOT - 1;
+    const int f = last ? (l.pv5 ? SLOTP * j + l.g8 : NCH) : SLOTP * j + l.g8;
+    const bool pv = last ? l.pv5 : true;
+    const bool valid = pv && l.rv;
+    const int xo_ = last ? l.xoff5 : l.xoff + j * SLOTP * PLANE;
+    const int wo_ = last ? l.woff5 : l.woff + j * SLOTP * 28;
+    const uint2 xb = *reinterpret_cast<const uint2*>(&sm.x[xo_]);
+    const float4 wa = *reinterpret_cast<const float4*>(&sm.w[0][wo_]);
+    const float4 wb = *reinterpret_cast<const float4*>(&sm.w[1][wo_]);
     float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w), w45 = make_float2(wb.x, wb.y);
     float w6 = wb.z;
-    const Row7 xn = cvt_row(xb);
+    const Row7 xo = cvt_row(xb);
+    Row7 xn = xo;
     if (UPDATE) {
-      const bool special = act >= 0 && (f == act || f == NCH);
-      Row7 xo = xn;
-      if (special) {  // the pre-action features of this row
-        uint2 ob;
-        if (f == act) ob = is_end ? badd(xb, n4b_r) : bsub(xb, n4b_r);
-        else ob = is_end ? bsub(xb, chgb_r) : badd(xb, chgb_r);
-        xo = cvt_row(ob);
+      const bool isact = f == act;  // (act = -1 matches nothing)
+      const float m = isact ? sgn : 0.0f;
+      xn.a = __ffma2_rn(f2(m), dn4.a, xo.a);
+      xn.b = __ffma2_rn(f2(m), dn4.b, xo.b);
+      xn.c = __ffma2_rn(f2(m), dn4.c, xo.c);
+      xn.d = __fmaf_rn(m, dn4.d, xo.d);
+      if (isact && valid) *reinterpret_cast<uint2*>(&sm.x[xo_]) = is_end ? bsub(xb, n4b_r) : badd(xb, n4b_r);
+      if (last && wid == 2 && act >= 0) {  // warp-uniform: the owners of plane 70 (n_elig) and of cnt2[act]
+        if (f == NCH && pv) {
+          const int co = act * PLANE + (l.rv ? l.r : 6) * ROWPAD;
+          const uint2 cr = *reinterpret_cast<const uint2*>(&sm.cnt2[co]);
+          const uint32_t want = is_end ? 1u : 0u;
+          // cells of N2 u {cell} where `act` is eligible on grid' (cnt2 == 0, or == 1 when the call at cell ends)
+          const uint2 cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
+          const uint2 eb = is_end ? badd(xb, cg) : bsub(xb, cg);
+          xn = cvt_row(eb);
+          if (l.rv) {
+            *reinterpret_cast<uint2*>(&sm.x[xo_]) = eb;
+            *reinterpret_cast<uint2*>(&sm.cnt2[co]) = is_end ? bsub(cr, n2b_r) : badd(cr, n2b_r);
+          }
+        }
       }
 #define DCA_UPD2(W, G, XN, XO)                                            \
   {                                                                       \
@@ -173,21 +218,30 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const int g8, c
         ag.g6[j] = __fmaf_rn(td.sg, xo.d, ag.g6[j]);
       }
       if (valid) {
-        *reinterpret_cast<float4*>(&sm.w[0][row * 4]) = make_float4(w01.x, w01.y, w23.x, w23.y);
-        *reinterpret_cast<float4*>(&sm.w[1][row * 4]) = make_float4(w45.x, w45.y, w6, 0.0f);
+        *reinterpret_cast<float4*>(&sm.w[0][wo_]) = make_float4(w01.x, w01.y, w23.x, w23.y);
+        *reinterpret_cast<float4*>(&sm.w[1][wo_]) = make_float4(w45.x, w45.y, w6, 0.0f);
       }
     }
-    const float rs = valid ? rowdot2(xn, w01, w23, w45, w6) : 0.0f;
+    rs[j] = valid ? rowdot2(xn, w01, w23, w45, w6) : 0.0f;
     const float rg = rowdot2(xn, ag.g01[j], ag.g23[j], ag.g45[j], ag.g6[j]);
-    const float p = tree8_lanes(rs);
-    if (pv && r == 0) sm.P[f] = p;
-    if (j == 0) rg_acc = rv ? rg : 0.0f;
+    if (j == 0) rg_acc = l.rv ? rg : 0.0f;
     else if (valid) rg_acc = __fadd_rn(rg_acc, rg);
+  }
+  // plane sums: xor-butterfly 1,2,4 over the 8 lanes of a group, the six slots interleaved
+#pragma unroll
+  for (int s = 1; s < 8; s <<= 1) {
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) rs[j] = __fadd_rn(rs[j], __shfl_xor_sync(0xffffffffu, rs[j], s));
+  }
+  if (l.r == 0) {
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j)
+      if (j < NSLOT - 1 || l.pv5) sm.P[SLOTP * j + l.g8] = rs[j];
   }
   // warp sum of x.wg: xor-butterfly 1,2,4,8,16
 #pragma unroll
   for (int s = 1; s < 32; s <<= 1) rg_acc = __fadd_rn(rg_acc, __shfl_xor_sync(0xffffffffu, rg_acc, s));
-  if (lane_id() == 0) sm.Wg[warp_id()] = rg_acc;
+  if (lane_id() == 0) sm.Wg[wid] = rg_acc;
 }
 
 // V(s) = x.w from the plane sums; every lane keeps the butterfly siblings it
@@ -213,9 +267,9 @@ __device__ __forceinline__ VTree v_tree(const SmemF& sm) {
 }
 
 // q[k] for every candidate: dense dot of afterstate k in the FAST tree, by
-// substituting the channel plane and the n_elig plane.  All 16 lane groups of the
-// CTA take one candidate each per pass.
-__device__ __forceinline__ void q_eval(SmemF& sm, const VTree& vt, const int n, const bool is_end,
+// substituting the channel plane and the n_elig plane.  The 12 agent lane groups
+// take one candidate each per pass.
+__device__ __forceinline__ void q_eval(SmemF& sm, const Ev& ev, const VTree& vt, const int n, const bool is_end,
                                        const uint2 n4b_r, const uint2 n2b_r) {
   const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
   const int wfirst = (threadIdx.x >> 5) * 4;  // first lane group of this warp
@@ -226,10 +280,11 @@ __device__ __forceinline__ void q_eval(SmemF& sm, const VTree& vt, const int n, 
   const uint2 x70 = *reinterpret_cast<const uint2*>(&sm.x[NCH * PLANE + rc * ROWPAD]);
   const float4 e_a = *reinterpret_cast<const float4*>(&sm.w[0][(NCH * 7 + rc) * 4]);
   const float4 e_b = *reinterpret_cast<const float4*>(&sm.w[1][(NCH * 7 + rc) * 4]);
-  for (int base = 0; base + wfirst < n; base += 16) {  // warp-uniform trip count
+#pragma unroll 1
+  for (int base = 0; base + wfirst < n; base += SLOTP) {  // warp-uniform trip count
     const int k = base + grp;
     const bool valid = k < n;
-    const int ch = sm.cand[valid ? k : n - 1];
+    const int ch = ev.cand[valid ? k : n - 1];
     const int row = ch * 7 + rc;
     // channel plane: x' = x +- [cell in N4 \ {cell}]   (Gridfuncs.hs:212-217)
     uint2 xr = *reinterpret_cast<const uint2*>(&sm.x[ch * PLANE + rc * ROWPAD]);
@@ -244,16 +299,22 @@ __device__ __forceinline__ void q_eval(SmemF& sm, const VTree& vt, const int n, 
     const uint2 er = is_end ? badd(x70, cg) : bsub(x70, cg);
     const float rowE = rv ? rowdot2(cvt_row(er), make_float2(e_a.x, e_a.y), make_float2(e_a.z, e_a.w),
                                     make_float2(e_b.x, e_b.y), e_b.z) : 0.0f;
-    const float Pp = tree8_lanes(rowP);
-    const float Ep = tree8_lanes(rowE);
+    float Pp = rowP, Ep = rowE;
+#pragma unroll
+    for (int s = 1; s < 8; s <<= 1) {
+      Pp = __fadd_rn(Pp, __shfl_xor_sync(0xffffffffu, Pp, s));
+      Ep = __fadd_rn(Ep, __shfl_xor_sync(0xffffffffu, Ep, s));
+    }
     // substitute leaf (ch & 31) of the V tree
     const int lc = ch & 31, hi = ch >> 5;
     const float p0 = hi == 0 ? Pp : sm.P[lc];
     const float p1 = hi == 1 ? Pp : sm.P[lc + 32];
     const float p2 = hi == 2 ? Pp : (lc < 6 ? sm.P[lc + 64] : 0.0f);
+    const float s0 = __shfl_sync(0xffffffffu, vt.sib[0], lc), s1 = __shfl_sync(0xffffffffu, vt.sib[1], lc),
+                s2 = __shfl_sync(0xffffffffu, vt.sib[2], lc), s3 = __shfl_sync(0xffffffffu, vt.sib[3], lc),
+                s4 = __shfl_sync(0xffffffffu, vt.sib[4], lc);
     float b = __fadd_rn(__fadd_rn(p0, p1), p2);
-#pragma unroll
-    for (int i = 0; i < 5; ++i) b = __fadd_rn(b, __shfl_sync(0xffffffffu, vt.sib[i], lc));
+    b = __fadd_rn(b, s0); b = __fadd_rn(b, s1); b = __fadd_rn(b, s2); b = __fadd_rn(b, s3); b = __fadd_rn(b, s4);
     const float qv = __fadd_rn(b, Ep);
     if (r == 0 && valid) sm.q[k] = qv;
   }
@@ -261,20 +322,25 @@ __device__ __forceinline__ void q_eval(SmemF& sm, const VTree& vt, const int n, 
 
 // argpmax (AccUtils.hs:203-208): the largest value, the LAST index among equals;
 // NaNs follow the sequential right fold exactly.  Every warp computes it for itself.
-__device__ __forceinline__ int argmax_last_warp(const float* q, int n) {
+__device__ __forceinline__ int argmax_last_warp(const float* q, int n, float& qbest) {
   const int lane = lane_id();
   float bq = -CUDART_INF_F;
   int bk = -1;
-  bool nan = false;
-  for (int k = lane; k < n; k += 32) {
-    const float v = q[k];
-    nan |= (v != v);
-    if (v >= bq) { bq = v; bk = k; }
+  if (n <= 32) {
+    if (lane < n) { bq = q[lane]; bk = lane; }
+  } else {
+#pragma unroll 1
+    for (int k = lane; k < n; k += 32) {
+      const float v = q[k];
+      if (v >= bq || v != v) { bq = v; bk = k; }  // (a NaN is kept so that the slow path is taken)
+    }
   }
-  if (__any_sync(0xffffffffu, nan)) {
+  if (__any_sync(0xffffffffu, bq != bq)) {
     int best = n - 1;
+#pragma unroll 1
     for (int i = n - 2; i >= 0; --i)
       if (q[i] > q[best]) best = i;
+    qbest = q[best];
     return best;
   }
   // order-preserving map float -> uint32, then two warp reductions
@@ -283,50 +349,38 @@ __device__ __forceinline__ int argmax_last_warp(const float* q, int n) {
   if (bq == 0.0f) u = 0x80000000u;  // -0 == +0
   if (bk < 0) u = 0u;
   const uint32_t m = __reduce_max_sync(0xffffffffu, u);
-  return __reduce_max_sync(0xffffffffu, (u == m) ? bk : -1);
+  const int k = __reduce_max_sync(0xffffffffu, (u == m) ? bk : -1);
+  qbest = __shfl_sync(0xffffffffu, bq, k & 31);
+  return k;
 }
 
-// Which cells change their n_elig feature when `ch` is (de)allocated at the event
-// cell (Gridfuncs.hs:220-232): members of N2 u {cell} with cnt2 == 0 (NEW/HOFF) or
-// cnt2 == 1 (END).  One warp.
-__device__ __forceinline__ unsigned long long elig_change_mask(const SmemF& sm, int ch, bool is_end,
-                                                               unsigned long long n2mask) {
-  const int lane = lane_id();
-  const uint8_t want = is_end ? 1 : 0;
-  const int c0 = lane, c1 = lane + 32;
-  const bool b0 = ((n2mask >> c0) & 1ULL) && sm.cnt2[ch * PLANE + c_tab.pos[c0]] == want;
-  const bool b1 = (c1 < NCELL) && ((n2mask >> c1) & 1ULL) && sm.cnt2[ch * PLANE + c_tab.pos[c1]] == want;
-  const unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
-  return (unsigned long long)lo | ((unsigned long long)hi << 32);
-}
-
-// executeAction (Gridfuncs.hs:105-110) + the in-place move of frep / cnt2 to the
-// chosen afterstate (`ssFrep .= nextFrep`, SimRunner.hs:90).  Warp 0.
-__device__ __forceinline__ void apply_action(SmemF& sm, int cell, bool is_end, int ch, const uint2 n4b_r,
-                                             const uint2 n2b_r) {
-  const int lane = lane_id();
-  const unsigned long long chg = elig_change_mask(sm, ch, is_end, c_tab.n2incl[cell]);
-  const int r = lane & 7, job = lane >> 3;
-  const uint2 chg_r = r < 7 ? spread7((uint32_t)(chg >> (7 * r)) & 0x7Fu) : make_uint2(0, 0);
-  if (lane < 8) sm.chgb[lane] = chg_r;
-  if (lane == 0) {
-    sm.chgmask = chg;
-    const uint32_t bit = 1u << (ch & 31);
-    if (is_end) sm.grid[cell][ch >> 5] &= ~bit;
-    else sm.grid[cell][ch >> 5] |= bit;
+// what every thread derives from the Q phase: the action and the TD scalars
+struct Decision {
+  int act;
+  float tderr;
+  TdScalars td;
+};
+__device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const VTree& vt, int n, bool is_end,
+                                           float& avgR, int& ncalls, float alpha_net, float alpha_avg,
+                                           float alpha_grad) {
+  Decision d;
+  d.act = -1;
+  float next_val = vt.val;  // no action: nextFrep = frep (Simulator.hs:170-171)
+  if (n > 0) {
+    const int k = argmax_last_warp(sm.q, n, next_val);  // selectAction, Simulator.hs:202
+    d.act = ev.cand[k];
+    ncalls += is_end ? -1 : 1;  // gridStep, Simulator.hs:137-144
   }
-  if (r < 7 && job < 3) {
-    if (job == 0) {  // in-use feature of ch at every cell of N4 \ {cell}
-      uint2* p = reinterpret_cast<uint2*>(&sm.x[ch * PLANE + r * ROWPAD]);
-      *p = is_end ? bsub(*p, n4b_r) : badd(*p, n4b_r);
-    } else if (job == 1) {  // n_elig feature on the changing cells
-      uint2* p = reinterpret_cast<uint2*>(&sm.x[NCH * PLANE + r * ROWPAD]);
-      *p = is_end ? badd(*p, chg_r) : bsub(*p, chg_r);
-    } else {  // cnt2 of ch over N2 u {cell}
-      uint2* p = reinterpret_cast<uint2*>(&sm.cnt2[ch * PLANE + r * ROWPAD]);
-      *p = is_end ? bsub(*p, n2b_r) : badd(*p, n2b_r);
-    }
-  }
+  // backward scalars (Agent.hs:62-67,75,78)
+  const float reward = (float)ncalls;  // boolSum nextGrid
+  d.tderr = __fsub_rn(__fadd_rn(__fsub_rn(reward, avgR), next_val), vt.val);
+  const float c = __fmul_rn(-2.0f, alpha_net);
+  d.td.ctd = __fmul_rn(c, d.tderr);
+  d.td.cavg = __fmul_rn(c, avgR);
+  d.td.ncdot = -__fmul_rn(c, vt.dotg);
+  d.td.sg = __fmul_rn(alpha_grad, __fsub_rn(d.tderr, vt.dotg));
+  avgR = __fadd_rn(avgR, __fmul_rn(alpha_avg, d.tderr));
+  return d;
 }
 
 // ---------------------------------------------------------------------------
@@ -341,8 +395,9 @@ struct EvRegs {
   int ren_from, ren_to;                 // pending reassign (EventGen.hs:62-72) as q_key values; -1 = none
   unsigned long long pt;                // pre-scan: min (time, id) over the stored queue
   unsigned pid, pslot;
-  unsigned long long dword;             // per lane: random word of draw ndraws + lane
-  double dnl;                           // per lane: -log(u) of that word
+  unsigned long long dbase;             // cached draws: lane l holds draw dbase + l ...
+  unsigned long long dword;             // ... its random word (per lane)
+  double dnl;                           // ... and -log(u) of that word (per lane)
   // random source
   int rng_mode;
   uint32_t k0, k1;
@@ -357,9 +412,11 @@ __device__ __forceinline__ unsigned long long ev_word(const EvRegs& e, unsigned 
   if (!e.tape_len) return 0ULL;
   return e.tape_w[d >= e.tape_len ? e.tape_len - 1 : d];
 }
-// lane l computes draw ndraws + l (word and -log u): all the draws an event can need
+// make sure draws ndraws .. ndraws + 3 are cached: one refill serves ~19 events
 __device__ __forceinline__ void ev_draws(EvRegs& e) {
-  const unsigned long long d = e.ndraws + (unsigned long long)lane_id();
+  if (e.ndraws >= e.dbase && e.ndraws + 4 <= e.dbase + 32) return;  // warp-uniform
+  e.dbase = e.ndraws;
+  const unsigned long long d = e.dbase + (unsigned long long)lane_id();
   if (e.rng_mode == RNG_PHILOX) {
     e.dword = philox_word(d, e.stream, e.k0, e.k1);
     e.dnl = neglog_u53(e.dword);
@@ -372,93 +429,132 @@ __device__ __forceinline__ void ev_draws(EvRegs& e) {
     e.dnl = 0.0;
   }
 }
+// draw ndraws + k: its word / its -log(u)   (k < 4 is always cached after ev_draws)
+__device__ __forceinline__ unsigned long long ev_draw_word(const EvRegs& e, unsigned k) {
+  const unsigned long long i = e.ndraws + k - e.dbase;
+  const unsigned long long w = __shfl_sync(0xffffffffu, e.dword, (int)(i & 31));
+  return i < 32 ? w : ev_word(e, e.ndraws + k);
+}
+__device__ __forceinline__ double ev_draw_nl(const EvRegs& e, unsigned k) {
+  return __shfl_sync(0xffffffffu, e.dnl, (int)((e.ndraws + k - e.dbase) & 31));
+}
 
-// candidate channels of the event (getAction, Simulator.hs:161-165), ascending
-// (indicesOf, AccUtils.hs:233-240), and the row byte masks of the event cell
-__device__ __forceinline__ void ev_candidates(SmemF& sm) {
+// candidate channels of event `ev` (getAction, Simulator.hs:161-165), ascending
+// (indicesOf, AccUtils.hs:233-240), and the row byte masks of its cell.  Runs while
+// the agents move cnt2[act] to the afterstate, so channel `act` is judged from the
+// grid (which this warp owns and has already updated) instead of cnt2.
+__device__ __forceinline__ void ev_candidates(const SmemF& sm, Ev& ev, const int act) {
   const int lane = lane_id();
-  const int cell = sm.ev.cell;
-  const bool is_end = sm.ev.type == EV_END;
+  const int cell = ev.cell;
+  const bool is_end = ev.type == EV_END;
   const int pos = c_tab.pos[cell];
+  const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
   uint32_t m[3];
   if (is_end) {  // inuseChs, Gridfuncs.hs:86-87
     m[0] = sm.grid[cell][0]; m[1] = sm.grid[cell][1]; m[2] = sm.grid[cell][2];
-  } else {       // eligibleChs, Gridfuncs.hs:69-82  <=>  cnt2 == 0
+  } else {       // eligibleChs, Gridfuncs.hs:69-82  <=>  nobody within distance 2 (incl. the cell) uses ch
+    bool act_free = true;
+    if (act >= 0) {
+      const int c1 = lane + 32;
+      const bool u0 = ((n2 >> lane) & 1ULL) && ((sm.grid[lane][act >> 5] >> (act & 31)) & 1u);
+      const bool u1 = c1 < NCELL && ((n2 >> c1) & 1ULL) && ((sm.grid[c1][act >> 5] >> (act & 31)) & 1u);
+      act_free = !__any_sync(0xffffffffu, u0 || u1);
+    }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       const int ch = 32 * j + lane;
-      const bool el = (ch < NCH) && (sm.cnt2[ch * PLANE + pos] == 0);
+      bool el = false;
+      if (ch < NCH) el = ch == act ? act_free : sm.cnt2[ch * PLANE + pos] == 0;
       m[j] = __ballot_sync(0xffffffffu, el);
     }
   }
   int base = 0;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    if ((m[j] >> lane) & 1u) sm.cand[base + __popc(m[j] & ((1u << lane) - 1u))] = (uint8_t)(32 * j + lane);
+    if ((m[j] >> lane) & 1u) ev.cand[base + __popc(m[j] & ((1u << lane) - 1u))] = (uint8_t)(32 * j + lane);
     base += __popc(m[j]);
   }
-  const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
   if (lane < 8) {
-    sm.n4b[lane] = (lane < 7) ? spread7((uint32_t)(n4 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
-    sm.n2b[lane] = (lane < 7) ? spread7((uint32_t)(n2 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
+    ev.n4b[lane] = (lane < 7) ? spread7((uint32_t)(n4 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
+    ev.n2b[lane] = (lane < 7) ? spread7((uint32_t)(n2 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
   }
-  if (lane == 0) {
-    sm.ev.ncand = base;
-    sm.n4mask = n4;
-    sm.n2mask = n2;
-  }
+  if (lane == 0) ev.ncand = base;
+  __syncwarp();
 }
 
-// pre-scan of the stored queue: argmin over (time, id) (pop, EventGen.hs:39-50),
-// applying the pending re-key of `reassign` on the way
+// the pending re-key of `reassign` (EventGen.hs:62-72)
+__device__ __forceinline__ void ev_rename(SmemF& sm, EvRegs& e) {
+  if (e.ren_from < 0) return;
+  const unsigned total = QNEW + e.n_end;
+  const uint16_t want = (uint16_t)e.ren_from, to = (uint16_t)e.ren_to;
+#pragma unroll 2
+  for (unsigned i = QNEW + lane_id(); i < total; i += 32)
+    if (sm.q_key[i] == want) sm.q_key[i] = to;
+  e.ren_from = -1;
+  __syncwarp();
+}
+
+// pre-scan of the stored queue: argmin over (time, id) (pop, EventGen.hs:39-50)
 __device__ __forceinline__ void ev_prescan(SmemF& sm, EvRegs& e) {
+  ev_rename(sm, e);
   const unsigned total = QNEW + e.n_end;
   const int lane = lane_id();
   unsigned long long bt = 0xFFFFFFFFFFFFFFFFULL;
   unsigned bid = 0xFFFFFFFFu, bslot = 0xFFFFFFFFu;
-  if (e.ren_from >= 0) {
-    const uint16_t want = (uint16_t)e.ren_from, to = (uint16_t)e.ren_to;
-    for (unsigned i = QNEW + lane; i < total; i += 32)
-      if (sm.q_key[i] == want) sm.q_key[i] = to;
-    e.ren_from = -1;
-  }
+  bool tie = false;
+#pragma unroll 4
   for (unsigned i = lane; i < total; i += 32) {
     const unsigned long long t = (unsigned long long)__double_as_longlong(sm.q_time[i]);
-    const unsigned id = sm.q_id[i];
-    if (t < bt || (t == bt && id < bid)) { bt = t; bid = id; bslot = i; }
+    tie |= (t == bt);
+    if (t < bt) { bt = t; bslot = i; }
   }
   const unsigned hi = (unsigned)(bt >> 32), lo = (unsigned)bt;
   const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
   bool ok = (hi == mhi);
   const unsigned mlo = __reduce_min_sync(0xffffffffu, ok ? lo : 0xFFFFFFFFu);
   ok = ok && (lo == mlo);
-  const unsigned mid = __reduce_min_sync(0xffffffffu, ok ? bid : 0xFFFFFFFFu);
-  ok = ok && (bid == mid);
-  const unsigned src = __ffs(__ballot_sync(0xffffffffu, ok)) - 1;
+  const unsigned okm = __ballot_sync(0xffffffffu, ok);
+  unsigned mid, src;
+  if (__any_sync(0xffffffffu, tie) || (okm & (okm - 1))) {
+    // equal times somewhere (practically never): redo the scan on (time, id) exactly
+    bt = 0xFFFFFFFFFFFFFFFFULL;
+#pragma unroll 1
+    for (unsigned i = lane; i < total; i += 32) {
+      const unsigned long long t = (unsigned long long)__double_as_longlong(sm.q_time[i]);
+      const unsigned id = sm.q_id[i];
+      if (t < bt || (t == bt && id < bid)) { bt = t; bid = id; bslot = i; }
+    }
+    ok = bt == (((unsigned long long)mhi << 32) | mlo);
+    mid = __reduce_min_sync(0xffffffffu, ok ? bid : 0xFFFFFFFFu);
+    ok = ok && (bid == mid);
+    src = __ffs(__ballot_sync(0xffffffffu, ok)) - 1;
+  } else {
+    src = __ffs(okm) - 1;
+    mid = sm.q_id[__shfl_sync(0xffffffffu, bslot, src)];
+  }
   e.pt = ((unsigned long long)mhi << 32) | mlo;
   e.pid = mid;
   e.pslot = __shfl_sync(0xffffffffu, bslot, src);
 }
 
-// what the event warp prepares for the event in sm.ev while the agents run the
-// dense pass: candidate channels, queue pre-scan, random draws
-__device__ __forceinline__ void ev_prepare(SmemF& sm, EvRegs& e) {
-  ev_candidates(sm);
-  const int type = sm.ev.type;
-  const bool pops = !(type == EV_END && sm.ev.hoff != HOFF_NONE);
-  if (pops || e.ren_from >= 0) ev_prescan(sm, e);
+// what the event warp does for event `ev` while the agents evaluate its candidates:
+// queue pre-scan (unless the next event is already known) and random draws
+__device__ __forceinline__ void ev_prepare(SmemF& sm, EvRegs& e, const Ev& ev) {
+  const int type = ev.type;
+  const bool pops = !(type == EV_END && ev.hoff != HOFF_NONE);
+  if (pops) ev_prescan(sm, e);
+  else ev_rename(sm, e);
   if (type != EV_END) ev_draws(e);
-  __syncwarp();
 }
 
-// environmentStep (Simulator.hs:101-134) for the event in the registers
-// (type, cell, ev_ch, ev_hoff, time) and the action `act` (-1 = Nothing);
-// leaves the next event in sm.ev.
-__device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, const int type, const int cell,
+// environmentStep (Simulator.hs:101-134) for the event (type, cell, ev_ch,
+// ev_hoff, time) and the action `act` (-1 = Nothing); writes the next event to `nx`.
+__device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx, const int type, const int cell,
                                                     const int ev_ch, const int ev_hoff, const double time,
                                                     const int act) {
   const int lane = lane_id();
-  if (lane == 0) {  // Stats hooks, Stats.hs:61-81 as called from Simulator.hs:105-114
+  if (lane == 0) {
+    // Stats hooks, Stats.hs:61-81 as called from Simulator.hs:105-114
     if (type == EV_NEW) {
       sm.stats[6]++; sm.stats[0]++;
       if (act >= 0) sm.stats[1]++;
@@ -469,6 +565,7 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, const 
     } else {
       sm.stats[4]++;
     }
+    if (act >= 0) sm.grid[cell][act >> 5] ^= 1u << (act & 31);  // executeAction, Gridfuncs.hs:105-110
   }
   bool have_new = false, have_end = false;
   unsigned long long t_new = 0, t_end = 0;
@@ -476,25 +573,23 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, const 
   int end_hoff = HOFF_NONE;
   if (type == EV_NEW) {
     // generateNewEvent, EventGen.hs:75-85: always, at time + Exp(mean_new)
-    const double nl0 = __shfl_sync(0xffffffffu, e.dnl, 0);
-    const double tn = __dadd_rn(time, __dmul_rn(nl0, e.mean_new));
+    const double tn = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 0), e.mean_new));
     t_new = (unsigned long long)__double_as_longlong(tn);
     id_new = e.next_id++;
     have_new = true;
     if (lane == 0) { sm.q_time[cell] = tn; sm.q_id[cell] = id_new; }
     unsigned used = 1;
     if (act >= 0) {
-      const unsigned long long w1 = __shfl_sync(0xffffffffu, e.dword, 1);
+      const unsigned long long w1 = ev_draw_word(e, 1);
       const double p = __dmul_rn((double)(w1 >> 11), 1.0 / 9007199254740992.0);  // Simulator.hs:121
-      const double nl2 = __shfl_sync(0xffffffffu, e.dnl, 2);
-      const double te = __dadd_rn(time, __dmul_rn(nl2, e.call_dur));  // callDurNew for both kinds, EventGen.hs:102,112
+      const double te = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 2), e.call_dur));  // callDurNew for both kinds, EventGen.hs:102,112
       used = 3;
       if (p < e.hoff_prob) {  // generateHoffNewEvent, EventGen.hs:94-109
         const int m = c_tab.n2cnt[cell];
         const int n_reject = 256 % m;
         int z;
         for (;;) {  // random-fu integralUniform on the low byte, with rejection
-          const unsigned long long wz = used < 32 ? __shfl_sync(0xffffffffu, e.dword, used) : ev_word(e, e.ndraws + used);
+          const unsigned long long wz = ev_draw_word(e, used);
           ++used;
           z = (int)(wz & 0xFFULL);
           if (z >= n_reject) break;
@@ -510,8 +605,7 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, const 
     e.ndraws += used;
   } else if (type == EV_HOFF) {
     if (act >= 0) {  // generateHoffEndEvent, EventGen.hs:114-116
-      const double nl0 = __shfl_sync(0xffffffffu, e.dnl, 0);
-      const double te = __dadd_rn(time, __dmul_rn(nl0, e.call_dur_hoff));
+      const double te = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 0), e.call_dur_hoff));
       t_end = (unsigned long long)__double_as_longlong(te);
       id_end = e.next_id++;
       have_end = true;
@@ -571,15 +665,16 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, const 
     }
   }
   if (lane == 0) {
-    sm.ev.time = nx_time; sm.ev.type = nx_type; sm.ev.cell = nx_cell; sm.ev.ch = nx_ch; sm.ev.hoff = nx_hoff;
+    nx.time = nx_time; nx.type = nx_type; nx.cell = nx_cell; nx.ch = nx_ch; nx.hoff = nx_hoff;
   }
   __syncwarp();
 }
 
 // order-independent hashes of grid and frep for the parity trace (same as
 // state_hashes); event warp only
-__device__ __forceinline__ void ev_hashes(const SmemF& sm, unsigned long long& hg_out, unsigned long long& hf_out) {
+__device__ __noinline__ void ev_hashes(const SmemF& sm, unsigned long long& hg_out, unsigned long long& hf_out) {
   unsigned long long hg = 0, hf = 0;
+#pragma unroll 1
   for (int i = lane_id(); i < NFEAT * NCELL; i += 32) {
     const int cell = i / NFEAT, f = i - cell * NFEAT;
     hf += (unsigned long long)sm.x[f * PLANE + c_tab.pos[cell]] * mix64(0x10000ULL + (unsigned long long)i);
@@ -594,10 +689,11 @@ __device__ __forceinline__ void ev_hashes(const SmemF& sm, unsigned long long& h
 }
 
 // violatesReuseConstraint (Gridfuncs.hs:94-101) and max(frep) > 70 (SimRunner.hs:150,158-159)
-__device__ __forceinline__ int ev_verify(const SmemF& sm, bool rc, bool nb) {
+__device__ __noinline__ int ev_verify(const SmemF& sm, bool rc, bool nb) {
   const int lane = lane_id();
   bool bad_rc = false, bad_nb = false;
   if (rc) {
+#pragma unroll 1
     for (int cell = lane; cell < NCELL; cell += 32) {
       unsigned long long nbm = c_tab.n2incl[cell] & ~(1ULL << cell);
       uint32_t o0 = 0, o1 = 0, o2 = 0;
@@ -609,8 +705,10 @@ __device__ __forceinline__ int ev_verify(const SmemF& sm, bool rc, bool nb) {
       bad_rc |= ((o0 & sm.grid[cell][0]) | (o1 & sm.grid[cell][1]) | (o2 & sm.grid[cell][2])) != 0;
     }
   }
-  if (nb)
+  if (nb) {
+#pragma unroll 1
     for (int i = lane; i < WPAD; i += 32) bad_nb |= sm.x[i] > 70;
+  }
   if (__any_sync(0xffffffffu, bad_rc)) return ST_REUSE_VIOLATED;
   if (__any_sync(0xffffffffu, bad_nb)) return ST_NELIG_OVERFLOW;
   return 0;
@@ -622,11 +720,13 @@ __device__ __forceinline__ int ev_verify(const SmemF& sm, bool rc, bool nb) {
 __device__ __forceinline__ void copy16(void* dst, const void* src, int bytes) {
   const uint4* s = reinterpret_cast<const uint4*>(src);
   uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll 1
   for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) d[i] = s[i];
 }
 __device__ __forceinline__ void copy8(void* dst, const void* src, int bytes) {
   const uint2* s = reinterpret_cast<const uint2*>(src);
   uint2* d = reinterpret_cast<uint2*>(dst);
+#pragma unroll 1
   for (int i = threadIdx.x; i < bytes / 8; i += blockDim.x) d[i] = s[i];
 }
 static_assert(sizeof(((RepState*)0)->x) % 8 == 0 && sizeof(((RepState*)0)->grid) % 16 == 0 &&
@@ -636,7 +736,9 @@ static_assert(sizeof(((RepState*)0)->x) % 8 == 0 && sizeof(((RepState*)0)->grid)
               offsetof(RepState, q_time) % 16 == 0 && offsetof(RepState, q_id) % 16 == 0 &&
               offsetof(RepState, q_key) % 16 == 0 && offsetof(RepState, q_hoff) % 8 == 0, "blob arrays");
 
-__device__ __forceinline__ void stage_in(SmemF& sm, Agent& ag, const RepState* g, int g8, int r) {
+// everything but wGradCorr (all threads of the CTA)
+__device__ __forceinline__ void stage_in(SmemF& sm, const RepState* g) {
+#pragma unroll 1
   for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
     const int f = row / 7, rr = row - 7 * f;
     const float4* src = reinterpret_cast<const float4*>(&g->w[f * PLANE + rr * ROWPAD]);
@@ -654,28 +756,14 @@ __device__ __forceinline__ void stage_in(SmemF& sm, Agent& ag, const RepState* g
   copy8(sm.q_hoff, g->q_hoff, sizeof sm.q_hoff);
   if (threadIdx.x < 8) sm.stats[threadIdx.x] = g->stats[threadIdx.x];
   if (threadIdx.x == 0) {
-    sm.ev.time = g->ev_time; sm.ev.type = g->ev_type; sm.ev.cell = g->ev_cell; sm.ev.ch = g->ev_ch;
-    sm.ev.hoff = g->ev_hoff; sm.ev.ncand = 0;
+    Ev& ev = sm.ev[0];
+    ev.time = g->ev_time; ev.type = g->ev_type; ev.cell = g->ev_cell; ev.ch = g->ev_ch; ev.hoff = g->ev_hoff;
+    ev.ncand = 0;
     sm.status = g->status;
-    sm.chgmask = 0;
-  }
-  if (threadIdx.x < NAGENT) {  // (warp-uniform: false for the whole event warp)
-    const int rc = r < 7 ? r : 6;
-#pragma unroll
-    for (int j = 0; j < NSLOT; ++j) {
-      int f = SLOTP * j + g8;
-      if (f > NCH) f = NCH;
-      const float4* src = reinterpret_cast<const float4*>(&g->wg[f * PLANE + rc * ROWPAD]);
-      const float4 a = src[0], b = src[1];
-      ag.g01[j] = make_float2(a.x, a.y);
-      ag.g23[j] = make_float2(a.z, a.w);
-      ag.g45[j] = make_float2(b.x, b.y);
-      ag.g6[j] = b.z;
-    }
   }
 }
-
-__device__ __forceinline__ void stage_out(const SmemF& sm, const Agent& ag, RepState* g, int g8, int r) {
+__device__ __forceinline__ void stage_out(const SmemF& sm, RepState* g) {
+#pragma unroll 1
   for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
     const int f = row / 7, rr = row - 7 * f;
     float4* dst = reinterpret_cast<float4*>(&g->w[f * PLANE + rr * ROWPAD]);
@@ -690,15 +778,31 @@ __device__ __forceinline__ void stage_out(const SmemF& sm, const Agent& ag, RepS
   copy16(g->q_key, sm.q_key, sizeof sm.q_key);
   copy8(g->q_hoff, sm.q_hoff, sizeof sm.q_hoff);
   if (threadIdx.x < 8) g->stats[threadIdx.x] = sm.stats[threadIdx.x];
-  if (threadIdx.x < NAGENT && r < 7) {
+}
+// wGradCorr rows of an agent lane
+__device__ __forceinline__ void load_wg(Agent& ag, const RepState* g, const Lane& l) {
+  const int rc = l.rv ? l.r : 6;
 #pragma unroll
-    for (int j = 0; j < NSLOT; ++j) {
-      const int f = SLOTP * j + g8;
-      if (f <= NCH) {
-        float4* dst = reinterpret_cast<float4*>(&g->wg[f * PLANE + r * ROWPAD]);
-        dst[0] = make_float4(ag.g01[j].x, ag.g01[j].y, ag.g23[j].x, ag.g23[j].y);
-        dst[1] = make_float4(ag.g45[j].x, ag.g45[j].y, ag.g6[j], 0.0f);
-      }
+  for (int j = 0; j < NSLOT; ++j) {
+    int f = SLOTP * j + l.g8;
+    if (f > NCH) f = NCH;
+    const float4* src = reinterpret_cast<const float4*>(&g->wg[f * PLANE + rc * ROWPAD]);
+    const float4 a = src[0], b = src[1];
+    ag.g01[j] = make_float2(a.x, a.y);
+    ag.g23[j] = make_float2(a.z, a.w);
+    ag.g45[j] = make_float2(b.x, b.y);
+    ag.g6[j] = b.z;
+  }
+}
+__device__ __forceinline__ void store_wg(const Agent& ag, RepState* g, const Lane& l) {
+  if (!l.rv) return;
+#pragma unroll
+  for (int j = 0; j < NSLOT; ++j) {
+    const int f = SLOTP * j + l.g8;
+    if (f <= NCH) {
+      float4* dst = reinterpret_cast<float4*>(&g->wg[f * PLANE + l.r * ROWPAD]);
+      dst[0] = make_float4(ag.g01[j].x, ag.g01[j].y, ag.g23[j].x, ag.g23[j].y);
+      dst[1] = make_float4(ag.g45[j].x, ag.g45[j].y, ag.g6[j], 0.0f);
     }
   }
 }
@@ -710,7 +814,7 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
   e.mean_new = g->mean_new; e.call_dur = g->call_dur; e.call_dur_hoff = g->call_dur_hoff; e.hoff_prob = g->hoff_prob;
   e.ren_from = -1; e.ren_to = -1;
   e.pt = 0xFFFFFFFFFFFFFFFFULL; e.pid = 0xFFFFFFFFu; e.pslot = 0;
-  e.dword = 0; e.dnl = 0.0;
+  e.dbase = 0xFFFFFFFFFFFFFFF0ULL; e.dword = 0; e.dnl = 0.0;  // (empty draw cache)
   e.rng_mode = a.rng_mode; e.k0 = a.key0; e.k1 = a.key1; e.stream = g->stream;
   e.tape_w = nullptr; e.tape_l = nullptr; e.tape_len = 0;
   if (a.rng_mode == RNG_TAPE && a.tape_off) {
@@ -724,68 +828,44 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
 // ---------------------------------------------------------------------------
 // The fused run kernel (dca_run, FAST order).  grid = n_replicas CTAs of 128.
 // The agent warps and the event warp run their own copies of the event loop
-// (separate register allocations) and meet at the three CTA barriers.
+// (separate register allocations) and meet at the CTA barriers.
+// sync_end (parity traces, verify flags): one more barrier per event so that the
+// event warp sees the afterstate before it hashes / verifies it.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" ::: "memory"); }
-
-// what every thread derives from the Q phase: the action and the TD scalars
-struct Decision {
-  int act;
-  float tderr;
-  TdScalars td;
-};
-__device__ __forceinline__ Decision decide(const SmemF& sm, const VTree& vt, int n, bool is_end, float& avgR,
-                                           int& ncalls, float alpha_net, float alpha_avg, float alpha_grad) {
-  Decision d;
-  d.act = -1;
-  float next_val = vt.val;  // no action: nextFrep = frep (Simulator.hs:170-171)
-  if (n > 0) {
-    const int k = argmax_last_warp(sm.q, n);  // selectAction, Simulator.hs:202
-    d.act = sm.cand[k];
-    next_val = sm.q[k];
-    ncalls += is_end ? -1 : 1;  // gridStep, Simulator.hs:137-144
-  }
-  // backward scalars (Agent.hs:62-67,75,78)
-  const float reward = (float)ncalls;  // boolSum nextGrid
-  d.tderr = __fsub_rn(__fadd_rn(__fsub_rn(reward, avgR), next_val), vt.val);
-  const float c = __fmul_rn(-2.0f, alpha_net);
-  d.td.ctd = __fmul_rn(c, d.tderr);
-  d.td.cavg = __fmul_rn(c, avgR);
-  d.td.ncdot = -__fmul_rn(c, vt.dotg);
-  d.td.sg = __fmul_rn(alpha_grad, __fsub_rn(d.tderr, vt.dotg));
-  avgR = __fadd_rn(avgR, __fmul_rn(alpha_avg, d.tderr));
-  return d;
-}
-
 template <bool TRACE>
 __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState* g) {
-  const int wid = warp_id();
-  const int g8 = threadIdx.x >> 3, r = threadIdx.x & 7, rc = r < 7 ? r : 6;
+  const bool sync_end = TRACE || a.verify_rc || a.verify_nb;
+  const Lane l = make_lane();
+  const int rc = l.rv ? l.r : 6;
   Agent ag;
-  stage_in(sm, ag, g, g8, r);
+  stage_in(sm, g);
+  load_wg(ag, g, l);
   float avgR = g->avg_reward;
   int ncalls = g->ncalls;
   const float alpha_net = g->alpha_net, alpha_avg = g->alpha_avg, alpha_grad = g->alpha_grad;
   cta_barrier();
-  dense_pass<false>(sm, ag, g8, r, -1, false, TdScalars{0.f, 0.f, 0.f, 0.f}, make_uint2(0, 0));
+  dense_pass<false>(sm, ag, l, -1, false, TdScalars{0.f, 0.f, 0.f, 0.f}, make_uint2(0, 0), make_uint2(0, 0));
   cta_barrier();  // B1
+#pragma unroll 1
   for (long long it = 0; it < a.max_events; ++it) {
-    const int cell = sm.ev.cell, n = sm.ev.ncand;
-    const bool is_end = sm.ev.type == EV_END;
-    const uint2 n4b_r = sm.n4b[rc], n2b_r = sm.n2b[rc];
+    const Ev& ev = sm.ev[it & 1];
+    const int n = ev.ncand;
+    const bool is_end = ev.type == EV_END;
+    const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
     // accFn1 = getAction (Simulator.hs:154-172)
     const VTree vt = v_tree(sm);
-    if (n > 0) q_eval(sm, vt, n, is_end, n4b_r, n2b_r);
+    if (n > 0) q_eval(sm, ev, vt, n, is_end, n4b_r, n2b_r);
     cta_barrier();  // B2
-    const Decision d = decide(sm, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
-    if (wid == 0 && d.act >= 0) apply_action(sm, cell, is_end, d.act, n4b_r, n2b_r);
-    cta_barrier();  // B3
-    // accFn2's dense part (Agent.hs:67-76) + the next event's sums
-    dense_pass<true>(sm, ag, g8, r, d.act, is_end, d.td, n4b_r);
+    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
+    // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
+    dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
+    if (sync_end) cta_barrier();
     cta_barrier();  // B1
     if (sm.status != ST_RUNNING) break;  // uniform
   }
-  stage_out(sm, ag, g, g8, r);
+  cta_barrier();  // (the event warp flushes a pending re-key before the queue is copied out)
+  stage_out(sm, g);
+  store_wg(ag, g, l);
   if (threadIdx.x == 0) {
     g->avg_reward = avgR;
     g->ncalls = ncalls;
@@ -794,30 +874,32 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
 
 template <bool TRACE>
 __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState* g, int rep) {
+  const bool sync_end = TRACE || a.verify_rc || a.verify_nb;
   const int lane = lane_id();
-  const int rc = (lane & 7) < 7 ? (lane & 7) : 6;
-  Agent none;  // (the event warp holds no weights)
-  stage_in(sm, none, g, 0, 0);
+  stage_in(sm, g);
   float avgR = g->avg_reward;
   int ncalls = g->ncalls;
   const float alpha_net = g->alpha_net, alpha_avg = g->alpha_avg, alpha_grad = g->alpha_grad;
   EvRegs e;
   ev_load(e, a, g, rep);
   cta_barrier();
-  ev_prepare(sm, e);
+  ev_candidates(sm, sm.ev[0], -1);
   cta_barrier();  // B1
-  for (long long it = 0; it < a.max_events; ++it) {
-    const int type = sm.ev.type, cell = sm.ev.cell, n = sm.ev.ncand;
-    const int ev_ch = sm.ev.ch, ev_hoff = sm.ev.hoff;
-    const double time = sm.ev.time;
+  long long it = 0;
+#pragma unroll 1
+  for (; it < a.max_events; ++it) {
+    const Ev& ev = sm.ev[it & 1];
+    Ev& nx = sm.ev[(it & 1) ^ 1];
+    const int type = ev.type, cell = ev.cell, n = ev.ncand;
+    const int ev_ch = ev.ch, ev_hoff = ev.hoff;
+    const double time = ev.time;
     const bool is_end = type == EV_END;
-    const uint2 n4b_r = sm.n4b[rc], n2b_r = sm.n2b[rc];
     const VTree vt = v_tree(sm);
-    if (n > 0) q_eval(sm, vt, n, is_end, n4b_r, n2b_r);
+    ev_prepare(sm, e, ev);
     cta_barrier();  // B2
-    const Decision d = decide(sm, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
-    ev_environment_step(sm, e, type, cell, ev_ch, ev_hoff, time, d.act);  // Simulator.hs:101-134
-    cta_barrier();  // B3
+    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
+    ev_environment_step(sm, e, nx, type, cell, ev_ch, ev_hoff, time, d.act);  // Simulator.hs:101-134
+    ev_candidates(sm, nx, d.act);
     e.iter += 1;  // Simulator.hs:131
     // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
     int stop = ST_RUNNING;
@@ -826,49 +908,56 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
       e.loss_sum = __fadd_rn(e.loss_sum, d.tderr);
       e.loss_n += 1;
     }
-    if (stop == ST_RUNNING && (a.verify_rc || a.verify_nb)) {
-      const int v = ev_verify(sm, a.verify_rc, a.verify_nb);
-      if (v) stop = v;
+    if (sync_end) {
+      cta_barrier();  // the agents have moved frep to the afterstate
+      if (stop == ST_RUNNING && (a.verify_rc || a.verify_nb)) {
+        const int v = ev_verify(sm, a.verify_rc, a.verify_nb);
+        if (v) stop = v;
+      }
+      if (TRACE && a.trace && e.iter - 1 < a.trace_cap) {
+        unsigned long long hg, hf;
+        ev_hashes(sm, hg, hf);
+        if (lane == 0) {
+          TraceRec& tr = a.trace[(size_t)rep * a.trace_cap + (e.iter - 1)];
+          tr.time = time;
+          tr.loss = d.tderr;
+          tr.avg_reward = avgR;
+          tr.reward = ncalls;
+          tr.etype = (uint8_t)type;
+          tr.cell = (uint8_t)cell;
+          tr.ch = (int8_t)d.act;
+          tr.ncand = (uint8_t)n;
+          tr.end_ch = (int8_t)(is_end ? ev_ch : -1);
+          for (int i = 0; i < 7; ++i) tr.pad[i] = 0;
+          tr.grid_hash = hg;
+          tr.frep_hash = hf;
+        }
+      }
     }
     if (stop == ST_RUNNING && e.min_loss > 0.0f && e.iter > 50 && fabsf(d.tderr) < e.min_loss) stop = ST_ZERO_LOSS;
     if (stop == ST_RUNNING && e.iter == e.n_events) stop = ST_SUCCESS;
     if (stop == ST_RUNNING && e.rng_mode == RNG_TAPE && e.ndraws + 8 > e.tape_len) stop = ST_TAPE_EXHAUSTED;
-    if (TRACE && a.trace && e.iter - 1 < a.trace_cap) {
-      unsigned long long hg, hf;
-      ev_hashes(sm, hg, hf);
-      if (lane == 0) {
-        TraceRec& tr = a.trace[(size_t)rep * a.trace_cap + (e.iter - 1)];
-        tr.time = time;
-        tr.loss = d.tderr;
-        tr.avg_reward = avgR;
-        tr.reward = ncalls;
-        tr.etype = (uint8_t)type;
-        tr.cell = (uint8_t)cell;
-        tr.ch = (int8_t)d.act;
-        tr.ncand = (uint8_t)n;
-        tr.end_ch = (int8_t)(is_end ? ev_ch : -1);
-        for (int i = 0; i < 7; ++i) tr.pad[i] = 0;
-        tr.grid_hash = hg;
-        tr.frep_hash = hf;
-      }
-    }
     if (lane == 0) sm.status = stop;
-    ev_prepare(sm, e);
     cta_barrier();  // B1
-    if (sm.status != ST_RUNNING) break;  // uniform
+    if (stop != ST_RUNNING) { ++it; break; }
   }
-  stage_out(sm, none, g, 0, 7);
+  ev_rename(sm, e);
+  cta_barrier();
+  stage_out(sm, g);
   if (lane == 0) {
+    const Ev& ev = sm.ev[it & 1];
     g->n_end = e.n_end; g->next_id = e.next_id; g->ndraws = e.ndraws;
     g->iter = e.iter; g->loss_n = e.loss_n; g->loss_sum = e.loss_sum;
-    g->ev_time = sm.ev.time; g->ev_type = sm.ev.type; g->ev_cell = sm.ev.cell; g->ev_ch = sm.ev.ch;
-    g->ev_hoff = sm.ev.hoff;
+    g->ev_time = ev.time; g->ev_type = ev.type; g->ev_cell = ev.cell; g->ev_ch = ev.ch; g->ev_hoff = ev.hoff;
     g->status = sm.status;
   }
 }
 
+#ifndef DCA_MIN_CTAS
+#define DCA_MIN_CTAS 5
+#endif
 template <bool TRACE>
-__global__ void __launch_bounds__(NT, 5) k_run_fast(RunArgs a) {
+__global__ void __launch_bounds__(NT, DCA_MIN_CTAS) k_run_fast(RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
   const int rep = blockIdx.x;
@@ -892,57 +981,47 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   RepState* g = states + rep;
   const bool is_end = is_end_i != 0;
   const int wid = warp_id(), lane = lane_id();
-  const int g8 = threadIdx.x >> 3, r = threadIdx.x & 7, rc = r < 7 ? r : 6;
+  const Lane l = make_lane();
+  const int rc = l.rv ? l.r : 6;
   Agent ag;
-  stage_in(sm, ag, g, g8, r);
+  stage_in(sm, g);
+  if (wid != EVW) load_wg(ag, g, l);
   float avgR = g->avg_reward;
   int ncalls = g->ncalls;
   __syncthreads();
-  const TdScalars td0{0.f, 0.f, 0.f, 0.f};
+  Ev& ev = sm.ev[0];
   if (wid == EVW) {
-    if (lane == 0) { sm.ev.cell = cell; sm.ev.type = is_end ? EV_END : EV_NEW; }
+    if (lane == 0) { ev.cell = cell; ev.type = is_end ? EV_END : EV_NEW; }
     __syncwarp();
-    ev_candidates(sm);
-    __syncwarp();
+    ev_candidates(sm, ev, -1);
     if (mode == 1 && lane == 0) {  // evaluate exactly the channel the caller executes
-      sm.ev.ncand = ch_in >= 0 ? 1 : 0;
-      sm.cand[0] = (uint8_t)(ch_in >= 0 ? ch_in : 0);
+      ev.ncand = ch_in >= 0 ? 1 : 0;
+      ev.cand[0] = (uint8_t)(ch_in >= 0 ? ch_in : 0);
     }
   } else {
-    dense_pass<false>(sm, ag, g8, r, -1, false, td0, make_uint2(0, 0));
+    dense_pass<false>(sm, ag, l, -1, false, TdScalars{0.f, 0.f, 0.f, 0.f}, make_uint2(0, 0), make_uint2(0, 0));
   }
   __syncthreads();
-  const int n = sm.ev.ncand;
-  const uint2 n4b_r = sm.n4b[rc], n2b_r = sm.n2b[rc];
+  const int n = ev.ncand;
+  const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
   const VTree vt = v_tree(sm);
-  if (n > 0) q_eval(sm, vt, n, is_end, n4b_r, n2b_r);
+  if (n > 0 && wid != EVW) q_eval(sm, ev, vt, n, is_end, n4b_r, n2b_r);
   __syncthreads();
-  int act = -1;
-  float next_val = vt.val;
-  if (n > 0) {
-    const int k = argmax_last_warp(sm.q, n);
-    act = sm.cand[k];
-    next_val = sm.q[k];
-  }
   if (mode == 0) {
+    float qb;
+    const int act = n > 0 ? ev.cand[argmax_last_warp(sm.q, n, qb)] : -1;
     if (threadIdx.x == 0) out->ch = act;
     return;
   }
-  if (act >= 0) ncalls += is_end ? -1 : 1;
-  const float reward = (float)ncalls;
-  const float tderr = __fsub_rn(__fadd_rn(__fsub_rn(reward, avgR), next_val), vt.val);
-  const float c = __fmul_rn(-2.0f, alpha_net);
-  TdScalars td;
-  td.ctd = __fmul_rn(c, tderr);
-  td.cavg = __fmul_rn(c, avgR);
-  td.ncdot = -__fmul_rn(c, vt.dotg);
-  td.sg = __fmul_rn(alpha_grad, __fsub_rn(tderr, vt.dotg));
-  avgR = __fadd_rn(avgR, __fmul_rn(alpha_avg, tderr));
-  if (wid == 0 && act >= 0) apply_action(sm, cell, is_end, act, n4b_r, n2b_r);
-  __syncthreads();
-  if (wid != EVW) dense_pass<true>(sm, ag, g8, r, act, is_end, td, n4b_r);
+  const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
+  if (wid == EVW) {
+    if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);
+  } else {
+    dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
+  }
   __syncthreads();
   // write back what the step changed (the event queue is untouched)
+#pragma unroll 1
   for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
     const int f = row / 7, rr = row - 7 * f;
     float4* dst = reinterpret_cast<float4*>(&g->w[f * PLANE + rr * ROWPAD]);
@@ -952,23 +1031,13 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   copy8(g->x, sm.x, sizeof sm.x);
   copy8(g->cnt2, sm.cnt2, sizeof sm.cnt2);
   copy16(g->grid, sm.grid, sizeof sm.grid);
-  if (threadIdx.x < NAGENT && r < 7) {
-#pragma unroll
-    for (int j = 0; j < NSLOT; ++j) {
-      const int f = SLOTP * j + g8;
-      if (f <= NCH) {
-        float4* dst = reinterpret_cast<float4*>(&g->wg[f * PLANE + r * ROWPAD]);
-        dst[0] = make_float4(ag.g01[j].x, ag.g01[j].y, ag.g23[j].x, ag.g23[j].y);
-        dst[1] = make_float4(ag.g45[j].x, ag.g45[j].y, ag.g6[j], 0.0f);
-      }
-    }
-  }
+  if (wid != EVW) store_wg(ag, g, l);
   if (threadIdx.x == 0) {
     g->avg_reward = avgR;
     g->ncalls = ncalls;
-    out->ch = act;
-    out->loss = tderr;
-    out->loss_is_nan = (tderr != tderr) ? 1 : 0;
+    out->ch = d.act;
+    out->loss = d.tderr;
+    out->loss_is_nan = (d.tderr != d.tderr) ? 1 : 0;
     out->reward = ncalls;
   }
 }
