@@ -407,27 +407,39 @@ struct EvRegs {
   unsigned long long tape_len;
 };
 
-__device__ __forceinline__ unsigned long long ev_word(const EvRegs& e, unsigned long long d) {
-  if (e.rng_mode == RNG_PHILOX) return philox_word(d, e.stream, e.k0, e.k1);
-  if (!e.tape_len) return 0ULL;
-  return e.tape_w[d >= e.tape_len ? e.tape_len - 1 : d];
+__device__ __noinline__ unsigned long long ev_word_cold(int rng_mode, uint32_t k0, uint32_t k1,
+                                                         unsigned long long stream, const unsigned long long* tape_w,
+                                                         unsigned long long tape_len, unsigned long long d) {
+  if (rng_mode == RNG_PHILOX) return philox_word(d, stream, k0, k1);
+  if (!tape_len) return 0ULL;
+  return tape_w[d >= tape_len ? tape_len - 1 : d];
 }
-// make sure draws ndraws .. ndraws + 3 are cached: one refill serves ~19 events
+__device__ __forceinline__ unsigned long long ev_word(const EvRegs& e, unsigned long long d) {
+  return ev_word_cold(e.rng_mode, e.k0, e.k1, e.stream, e.tape_w, e.tape_len, d);
+}
+// refill the draw cache: lane l <- draw dbase + l (cold: one refill serves ~19 events)
+__device__ __noinline__ void ev_refill(int rng_mode, uint32_t k0, uint32_t k1, unsigned long long stream,
+                                       const unsigned long long* tape_w, const double* tape_l,
+                                       unsigned long long tape_len, unsigned long long dbase,
+                                       unsigned long long* dword, double* dnl) {
+  const unsigned long long d = dbase + (unsigned long long)lane_id();
+  if (rng_mode == RNG_PHILOX) {
+    *dword = philox_word(d, stream, k0, k1);
+    *dnl = neglog_u53(*dword);
+  } else if (tape_len) {
+    const unsigned long long i = d >= tape_len ? tape_len - 1 : d;
+    *dword = tape_w[i];
+    *dnl = tape_l[i];
+  } else {
+    *dword = 0ULL;
+    *dnl = 0.0;
+  }
+}
+// make sure draws ndraws .. ndraws + 3 are cached
 __device__ __forceinline__ void ev_draws(EvRegs& e) {
   if (e.ndraws >= e.dbase && e.ndraws + 4 <= e.dbase + 32) return;  // warp-uniform
   e.dbase = e.ndraws;
-  const unsigned long long d = e.dbase + (unsigned long long)lane_id();
-  if (e.rng_mode == RNG_PHILOX) {
-    e.dword = philox_word(d, e.stream, e.k0, e.k1);
-    e.dnl = neglog_u53(e.dword);
-  } else if (e.tape_len) {
-    const unsigned long long i = d >= e.tape_len ? e.tape_len - 1 : d;
-    e.dword = e.tape_w[i];
-    e.dnl = e.tape_l[i];
-  } else {
-    e.dword = 0ULL;
-    e.dnl = 0.0;
-  }
+  ev_refill(e.rng_mode, e.k0, e.k1, e.stream, e.tape_w, e.tape_l, e.tape_len, e.dbase, &e.dword, &e.dnl);
 }
 // draw ndraws + k: its word / its -log(u)   (k < 4 is always cached after ev_draws)
 __device__ __forceinline__ unsigned long long ev_draw_word(const EvRegs& e, unsigned k) {
@@ -494,13 +506,33 @@ __device__ __forceinline__ void ev_rename(SmemF& sm, EvRegs& e) {
   __syncwarp();
 }
 
+__device__ __noinline__ void ev_prescan_exact(const double* q_time, const uint32_t* q_id, unsigned total,
+                                              unsigned long long tmin, unsigned* bslot_out, unsigned* mid_out,
+                                              unsigned* src_out) {
+  const int lane = lane_id();
+  unsigned long long bt = 0xFFFFFFFFFFFFFFFFULL;
+  unsigned bid = 0xFFFFFFFFu, bslot = 0xFFFFFFFFu;
+#pragma unroll 1
+  for (unsigned i = lane; i < total; i += 32) {
+    const unsigned long long t = (unsigned long long)__double_as_longlong(q_time[i]);
+    const unsigned id = q_id[i];
+    if (t < bt || (t == bt && id < bid)) { bt = t; bid = id; bslot = i; }
+  }
+  bool ok = bt == tmin;
+  const unsigned mid = __reduce_min_sync(0xffffffffu, ok ? bid : 0xFFFFFFFFu);
+  ok = ok && (bid == mid);
+  *bslot_out = bslot;
+  *mid_out = mid;
+  *src_out = __ffs(__ballot_sync(0xffffffffu, ok)) - 1;
+}
+
 // pre-scan of the stored queue: argmin over (time, id) (pop, EventGen.hs:39-50)
 __device__ __forceinline__ void ev_prescan(SmemF& sm, EvRegs& e) {
   ev_rename(sm, e);
   const unsigned total = QNEW + e.n_end;
   const int lane = lane_id();
   unsigned long long bt = 0xFFFFFFFFFFFFFFFFULL;
-  unsigned bid = 0xFFFFFFFFu, bslot = 0xFFFFFFFFu;
+  unsigned bslot = 0xFFFFFFFFu;
   bool tie = false;
 #pragma unroll 4
   for (unsigned i = lane; i < total; i += 32) {
@@ -517,17 +549,7 @@ __device__ __forceinline__ void ev_prescan(SmemF& sm, EvRegs& e) {
   unsigned mid, src;
   if (__any_sync(0xffffffffu, tie) || (okm & (okm - 1))) {
     // equal times somewhere (practically never): redo the scan on (time, id) exactly
-    bt = 0xFFFFFFFFFFFFFFFFULL;
-#pragma unroll 1
-    for (unsigned i = lane; i < total; i += 32) {
-      const unsigned long long t = (unsigned long long)__double_as_longlong(sm.q_time[i]);
-      const unsigned id = sm.q_id[i];
-      if (t < bt || (t == bt && id < bid)) { bt = t; bid = id; bslot = i; }
-    }
-    ok = bt == (((unsigned long long)mhi << 32) | mlo);
-    mid = __reduce_min_sync(0xffffffffu, ok ? bid : 0xFFFFFFFFu);
-    ok = ok && (bid == mid);
-    src = __ffs(__ballot_sync(0xffffffffu, ok)) - 1;
+    ev_prescan_exact(sm.q_time, sm.q_id, total, ((unsigned long long)mhi << 32) | mlo, &bslot, &mid, &src);
   } else {
     src = __ffs(okm) - 1;
     mid = sm.q_id[__shfl_sync(0xffffffffu, bslot, src)];
