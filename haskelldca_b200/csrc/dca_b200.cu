@@ -19,6 +19,7 @@
 
 #include "dca_kernels.cuh"
 #include "dca_fast.cuh"
+#include "dca_ops.cuh"
 
 using namespace dca;
 
@@ -784,11 +785,10 @@ int dca_gf_inc_afterstate_freps(int32_t device, int32_t r, int32_t c, int32_t is
   int rc = gf_begin(device, grid, g);
   if (rc) return rc;
   CK(cudaMemcpy(g.frep, frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
-  k_gf_load_frep<<<1, 256>>>(g.st, g.frep);
   CK(cudaMemcpy(g.chs, chs, sizeof(long long) * n, cudaMemcpyHostToDevice));
   long long* d_out = nullptr;
   CK(cudaMalloc(&d_out, sizeof(long long) * (size_t)n * FREP));
-  k_gf_inc_afterstate_freps<<<148, 256>>>(g.st, r * COLS + c, is_end, g.chs, n, d_out);
+  k_gf_inc_afterstate_freps<<<148, 256>>>(g.st, r * COLS + c, is_end, g.chs, n, g.frep, d_out);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(long long) * (size_t)n * FREP, cudaMemcpyDeviceToHost);
   cudaFree(d_out);
@@ -808,6 +808,131 @@ int dca_gf_violates_reuse_constraint(int32_t device, const uint8_t* grid, int32_
   int v = 0;
   CK(cudaMemcpy(&v, g.n, sizeof(int), cudaMemcpyDeviceToHost));
   *violates = v;
+  return DCA_OK;
+}
+
+
+}  // extern "C"
+
+// ---- accFn1 / accFn2 on explicit arrays (SimRunner.hs:61-62) --------------------
+namespace {
+struct DevBuf {  // RAII device scratch
+  void* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  template <typename T> T* as() { return static_cast<T*>(p); }
+};
+int dev_alloc(DevBuf& b, size_t bytes) {
+  dca_handle* h = nullptr;
+  CK(cudaMalloc(&b.p, bytes ? bytes : 1));
+  return DCA_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int dca_acc_get_action(int32_t device, int32_t order, int32_t r, int32_t c, int32_t is_end, const float* wnet,
+                       const uint8_t* grid, const int64_t* frep, int32_t* ch, int64_t* next_frep) {
+  dca_handle* h = nullptr;
+  if (r < 0 || r >= ROWS || c < 0 || c >= COLS || !wnet || !frep || !ch || !next_frep ||
+      (order != DCA_ORDER_REF && order != DCA_ORDER_FAST))
+    return fail(h, DCA_ERR_ARG, "dca_acc_get_action: bad argument");
+  GfScratch g;
+  int rc = gf_begin(device, grid, g);
+  if (rc) return rc;
+  const int cell = r * COLS + c;
+  k_gf_chs<<<1, 32>>>(g.st, cell, is_end, g.chs, g.n);  // eligibleChs / inuseChs, Simulator.hs:161-165
+  CK(cudaGetLastError());
+  int n = 0;
+  CK(cudaMemcpy(&n, g.n, sizeof(int), cudaMemcpyDeviceToHost));
+  if (n == 0) {  // (Nothing, frep), Simulator.hs:170-171
+    *ch = -1;
+    memcpy(next_frep, frep, sizeof(int64_t) * FREP);
+    return DCA_OK;
+  }
+  DevBuf afreps, w, q, idx;
+  if ((rc = dev_alloc(afreps, sizeof(long long) * (size_t)n * FREP)) || (rc = dev_alloc(w, sizeof(float) * FREP)) ||
+      (rc = dev_alloc(q, sizeof(float) * NCH)) || (rc = dev_alloc(idx, sizeof(int))))
+    return rc;
+  CK(cudaMemcpy(g.frep, frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(w.p, wnet, sizeof(float) * FREP, cudaMemcpyHostToDevice));
+  // selectAction, Simulator.hs:185-205: afterstate freps -> q = mvMul -> argpmax
+  k_gf_inc_afterstate_freps<<<148, 256>>>(g.st, cell, is_end, g.chs, n, g.frep, afreps.as<long long>());
+  ops::k_dense_dots<<<n, ops::NT>>>(order, afreps.as<long long>(), n, w.as<float>(), q.as<float>());
+  ops::k_argpmax<<<1, 32>>>(q.as<float>(), n, idx.as<int>());
+  CK(cudaGetLastError());
+  int k = 0;
+  CK(cudaMemcpy(&k, idx.p, sizeof(int), cudaMemcpyDeviceToHost));
+  long long chs[NCH];
+  CK(cudaMemcpy(chs, g.chs, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(next_frep, afreps.as<long long>() + (size_t)k * FREP, sizeof(long long) * FREP, cudaMemcpyDeviceToHost));
+  *ch = (int32_t)chs[k];
+  return DCA_OK;
+}
+
+int dca_acc_grid_step_train(int32_t device, int32_t order, float alpha_net, float alpha_avg, float alpha_grad,
+                            int32_t is_end, int32_t r, int32_t c, int32_t ch, const int64_t* frep,
+                            const int64_t* next_frep, uint8_t* grid, float* wnet, float* wgrad, float* avg_reward,
+                            float* loss, int32_t* loss_is_nan, int64_t* reward) {
+  dca_handle* h = nullptr;
+  if (r < 0 || r >= ROWS || c < 0 || c >= COLS || ch >= NCH || !frep || !next_frep || !grid || !wnet || !wgrad ||
+      !avg_reward || (order != DCA_ORDER_REF && order != DCA_ORDER_FAST))
+    return fail(h, DCA_ERR_ARG, "dca_acc_grid_step_train: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, DCA_ERR_NO_DEVICE, "dca_acc_grid_step_train: no CUDA device (there is no CPU fallback)");
+  int rc = set_device(h, device);
+  if (rc) return rc;
+  DevBuf dgrid, df, dnf, dw, dg, drew, dout;
+  if ((rc = dev_alloc(dgrid, DCA_GRID_SIZE)) || (rc = dev_alloc(df, sizeof(long long) * FREP)) ||
+      (rc = dev_alloc(dnf, sizeof(long long) * FREP)) || (rc = dev_alloc(dw, sizeof(float) * FREP)) ||
+      (rc = dev_alloc(dg, sizeof(float) * FREP)) || (rc = dev_alloc(drew, sizeof(long long))) ||
+      (rc = dev_alloc(dout, sizeof(ops::BackwardOut))))
+    return rc;
+  CK(cudaMemcpy(dgrid.p, grid, DCA_GRID_SIZE, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(df.p, frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dnf.p, next_frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw.p, wnet, sizeof(float) * FREP, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dg.p, wgrad, sizeof(float) * FREP, cudaMemcpyHostToDevice));
+  // gridStep, Simulator.hs:137-144
+  ops::k_grid_step<<<1, 256>>>(dgrid.as<uint8_t>(), r * COLS + c, is_end, ch, drew.as<long long>());
+  CK(cudaGetLastError());
+  long long rew = 0;
+  CK(cudaMemcpy(&rew, drew.p, sizeof rew, cudaMemcpyDeviceToHost));
+  // backward, Agent.hs:44-81 with reward' = fromIntegral reward (SimRunner.hs:117)
+  ops::k_backward<<<1, ops::NT>>>(order, alpha_net, alpha_avg, alpha_grad, df.as<long long>(), dnf.as<long long>(),
+                                  (float)rew, *avg_reward, dw.as<float>(), dg.as<float>(), dout.as<ops::BackwardOut>());
+  CK(cudaGetLastError());
+  ops::BackwardOut o;
+  CK(cudaMemcpy(&o, dout.p, sizeof o, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(grid, dgrid.p, DCA_GRID_SIZE, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(wnet, dw.p, sizeof(float) * FREP, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(wgrad, dg.p, sizeof(float) * FREP, cudaMemcpyDeviceToHost));
+  *avg_reward = o.avg_reward;
+  if (loss) *loss = o.loss;
+  if (loss_is_nan) *loss_is_nan = o.loss_is_nan;
+  if (reward) *reward = rew;
+  return DCA_OK;
+}
+
+int dca_dense_dot(int32_t device, int32_t order, int32_t grad_corr_tree, const int64_t* frep, const float* w, float* out) {
+  dca_handle* h = nullptr;
+  if (!frep || !w || !out || (order != DCA_ORDER_REF && order != DCA_ORDER_FAST))
+    return fail(h, DCA_ERR_ARG, "dca_dense_dot: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, DCA_ERR_NO_DEVICE, "dca_dense_dot: no CUDA device (there is no CPU fallback)");
+  int rc = set_device(h, device);
+  if (rc) return rc;
+  DevBuf df, dw, dq;
+  if ((rc = dev_alloc(df, sizeof(long long) * FREP)) || (rc = dev_alloc(dw, sizeof(float) * FREP)) ||
+      (rc = dev_alloc(dq, sizeof(float))))
+    return rc;
+  CK(cudaMemcpy(df.p, frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw.p, w, sizeof(float) * FREP, cudaMemcpyHostToDevice));
+  if (grad_corr_tree) ops::k_dense_dot_g<<<1, ops::NT>>>(order, df.as<long long>(), dw.as<float>(), dq.as<float>());
+  else ops::k_dense_dots<<<1, ops::NT>>>(order, df.as<long long>(), 1, dw.as<float>(), dq.as<float>());
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, dq.p, sizeof(float), cudaMemcpyDeviceToHost));
   return DCA_OK;
 }
 

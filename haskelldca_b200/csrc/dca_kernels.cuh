@@ -991,7 +991,7 @@ __global__ void k_gf_chs(const RepState* st, int cell, int is_end, long long* ch
 }
 // incAfterStateFreps (Gridfuncs.hs:186-252) in the cnt2 formulation
 __global__ void k_gf_inc_afterstate_freps(const RepState* st, int cell, int is_end,
-                                          const long long* chs, int n, long long* out) {
+                                          const long long* chs, int n, const long long* frep, long long* out) {
   const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
   const int diff = is_end ? -1 : 1;
   const uint8_t want = is_end ? 1 : 0;
@@ -1000,7 +1000,7 @@ __global__ void k_gf_inc_afterstate_freps(const RepState* st, int cell, int is_e
     int k = (int)(idx / FREP), i = (int)(idx - (long long)k * FREP);
     int c2 = i / NFEAT, f = i - c2 * NFEAT;
     int ch = (int)chs[k];
-    int v = st->x[f * PLANE + c_tab.pos[c2]];
+    long long v = frep[i];  // the caller's frep (it need not be featureRep grid), Gridfuncs.hs:206
     if (f == ch && ((n4 >> c2) & 1ULL)) v += diff;
     if (f == NCH && ((n2 >> c2) & 1ULL) && st->cnt2[ch * PLANE + c_tab.pos[c2]] == want) v -= diff;
     out[idx] = v;

@@ -180,6 +180,27 @@ int dca_grid_step_train(dca_handle *h, int32_t replica, float alpha_net, float a
                         float alpha_grad, int32_t is_end, int32_t r, int32_t c, int32_t ch,
                         float *loss, int32_t *loss_is_nan, int64_t *reward);
 
+/* ---- the same two operators on EXPLICIT arrays (pure functions) --------------- */
+/* accFn1 :: Scalar Cell -> Scalar Bool -> Agent -> Grid -> Frep -> (Scalar (Maybe Ch), Frep)
+ * exactly as runStep calls it (src/SimRunner.hs:61,75): candidates from `grid`
+ * (eligibleChs / inuseChs), afterstate freps from `frep` (incAfterStateFreps), q = mvMul with
+ * wnet, argpmax.  *ch = -1 and next_frep = frep when there is no candidate. */
+int dca_acc_get_action(int32_t device, int32_t order, int32_t r, int32_t c, int32_t is_end,
+                       const float *wnet, const uint8_t *grid, const int64_t *frep, int32_t *ch,
+                       int64_t *next_frep);
+/* accFn2 :: alphaN -> alphaA -> alphaG -> eIsEnd -> cell -> Maybe Ch -> frep -> nextFrep -> Grid -> Agent
+ *        -> (Grid, Agent, Scalar (Maybe Float), Scalar Int)          (src/SimRunner.hs:62,85-86,100-118)
+ * grid, wnet, wgrad and *avg_reward are updated in place; ch = -1 is Nothing. */
+int dca_acc_grid_step_train(int32_t device, int32_t order, float alpha_net, float alpha_avg,
+                            float alpha_grad, int32_t is_end, int32_t r, int32_t c, int32_t ch,
+                            const int64_t *frep, const int64_t *next_frep, uint8_t *grid, float *wnet,
+                            float *wgrad, float *avg_reward, float *loss, int32_t *loss_is_nan,
+                            int64_t *reward);
+/* vvMul (src/AccUtils.hs:219-220) = forward (src/Agent.hs:22-23) of one frep with one weight
+ * vector in the given order; grad_corr_tree != 0 selects the FAST tree of x . wGradCorr. */
+int dca_dense_dot(int32_t device, int32_t order, int32_t grad_corr_tree, const int64_t *frep,
+                  const float *w, float *out);
+
 /* ---- state read-back / write ----------------------------------------------- */
 /* any output pointer may be NULL */
 int dca_read_state(dca_handle *h, int32_t replica, uint8_t *grid, int64_t *frep, float *wnet,
