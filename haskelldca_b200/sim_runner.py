@@ -44,3 +44,9 @@ def run_sim(opt: Opt, out=print, replica: int = 0):
         return dict(status=status, state=state, summary=sims.read_summary(), device_ms=device_ms, wall_s=dt)
     finally:
         sims.close()
+
+
+if __name__ == "__main__":  # CLI analogue of `dca-exe` (src/Main.hs:10-22)
+    from .opt import get_opts
+
+    run_sim(get_opts())

@@ -82,3 +82,31 @@ def test_stats_reports_format():  # src/Stats.hs:83-152
     assert e.startswith("Finished 10000 events. Blocking probability 0.1099 for new calls.\n5520 new arrivals of which 607 have been rejected. 433 calls in progress")
     assert "SOME CALLS WERE LOST" not in e
     assert "SOME CALLS WERE LOST" in stats.stats_report_end(st, 432, 10000)
+
+
+def test_haskell_bindings_match_the_library():
+    """hs/DcaB200/*.hs cannot be compiled here (no GHC): pin what can be checked without it --
+    every `foreign import`ed symbol is exported, and the dca_config offsets poked by Fused.hs
+    are the C struct's (ctypes mirrors include/dca_b200.h)."""
+    import ctypes as C
+    import re
+
+    from haskelldca_b200 import _ffi
+
+    L = C.CDLL(_ffi.lib_path())
+    ffi_src = open(os.path.join(ROOT, "hs", "DcaB200", "FFI.hs")).read()
+    syms = set(re.findall(r'foreign import ccall safe "&?(\w+)"', ffi_src))
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(L, s), s
+        assert s in _ffi.SYMBOLS, s  # and it is declared in the header mirror
+    fused = open(os.path.join(ROOT, "hs", "DcaB200", "Fused.hs")).read()
+    offs = {k: int(v) for k, v in re.findall(r"\b(off\w+|sizeofConfig) = (\d+)", fused)}
+    want = {"offNReplicas": "n_replicas", "offSeed": "seed", "offRngMode": "rng_mode", "offOrder": "order",
+            "offNEvents": "n_events", "offMinLoss": "min_loss", "offVerifyRC": "verify_reuse_constraint",
+            "offVerifyNB": "verify_nelig_bounds", "offCallDur": "call_dur", "offCallDurHoff": "call_dur_hoff",
+            "offCallRate": "call_rate", "offHoffProb": "hoff_prob", "offAlphaNet": "alpha_net",
+            "offAlphaAvg": "alpha_avg", "offAlphaGrad": "alpha_grad"}
+    for hs_name, field in want.items():
+        assert offs[hs_name] == getattr(_ffi.Config, field).offset, hs_name
+    assert offs["sizeofConfig"] == C.sizeof(_ffi.Config)
