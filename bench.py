@@ -33,6 +33,17 @@ UNIT = "events/s"
 ALG_BYTES_PER_EVENT = 4 * 3479 * 4  # read+write of wNet and wGradCorr, SURVEY.md 8(d)
 
 
+def measured_traffic():
+    """DRAM bytes of one k_run_fast launch on the bench workload, from the committed ncu capture
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of `ncu --set full`)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_launch"]), t.get("source", "")
+    except Exception:
+        return None, "no ncu capture committed"
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -138,10 +149,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
     ap.add_argument("--events", type=int, default=100000, help="events per replica per step")
-    ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--hoff_prob", type=float, default=0.0)
-    ap.add_argument("--ref-events", type=int, default=4000, dest="ref_events")
-    ap.add_argument("--cpu-events", type=int, default=20000, dest="cpu_events")
+    ap.add_argument("--ref-events", type=int, default=100000, dest="ref_events")
+    ap.add_argument("--cpu-events", type=int, default=100000, dest="cpu_events")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -158,6 +168,7 @@ def main():
     import torch.distributed as dist
 
     from haskelldca_b200 import Opt, Replicas, _ffi
+    from haskelldca_b200.replica_shards import shard
 
     _ffi.load(build_if_missing=False)  # the prebuilt sm_100a library, or fail
     if not torch.cuda.is_available():
@@ -172,9 +183,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    n_rep, n_ev = args.replicas, args.events
+    n_ev = args.events
+    first, n_rep = shard(args.replicas * world, world, rank)  # weak scaling: args.replicas per GPU, contiguous blocks
     opt = Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=0, device=local_rank,
-              first_replica=rank * n_rep, hoff_prob=args.hoff_prob, warps_per_replica=args.warps)
+              first_replica=first, hoff_prob=args.hoff_prob)
     sims = Replicas(opt)
     state_mb = n_rep * 50960 / 1e6
 
@@ -249,6 +261,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
+        traffic, traffic_src = measured_traffic()
         per_gpu_run = n_rep * n_ev * args.steps / (run_ms_max / 1e3)  # the dominant kernel, per GPU
         achieved = per_gpu_run * ALG_BYTES_PER_EVENT / 1e9
         bp = float(st[2]) / (float(st[0]) + 1.0)
@@ -261,11 +274,14 @@ def main():
                        "replicas_per_gpu": n_rep, "events_per_replica": n_ev, "order": "fast", "rng": "philox",
                        "l2": f"inputs larger than L2 ({state_mb:.0f} MB of replica state per GPU vs 126 MB L2; state is re-initialised every step)",
                        "parallelism": f"{world} x independent replica shards, NCCL all-reduce of stats only"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "dca::k_run<ORDER_FAST>", "peak_source": peak_src,
-                         "note": "achieved = events/s/GPU x 55 664 algorithmic bytes (r+w of wNet, wGradCorr per event); the kernel keeps a replica's "
-                                 "weights in shared memory for the whole launch, so DRAM traffic is ~100 KB per replica per launch and frac > 1 is "
-                                 "legitimate multi-event residency (see profiles/ for ncu dram bytes and issue utilisation)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "dca::fast::k_run_fast<false>", "peak_source": peak_src, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": n_rep * n_ev * ALG_BYTES_PER_EVENT,
+                         "note": "achieved = events/s/GPU x 55 664 algorithmic bytes (r+w of wNet, wGradCorr per event, Agent.hs:67-76) over the "
+                                 "kernel's own CUDA-event duration; the kernel keeps a replica's weights on chip (shared memory + registers) for "
+                                 "the whole launch, so DRAM traffic is one state blob in and out per replica per launch and frac > 1 is "
+                                 "legitimate multi-event residency -- the binding limits are issue slots and the per-event dependency chain "
+                                 "(profiles/: smsp__issue_active, stall reasons)"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -5,8 +5,7 @@ from haskelldca_b200 import Opt, Replicas
 
 n_rep = int(sys.argv[1]) if len(sys.argv) > 1 else 592
 n_ev = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
-warps = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", warps_per_replica=warps)) as s:
+with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox")) as s:
     for _ in range(2):
         s.reset()
         ms = s.run(n_ev)
