@@ -98,6 +98,14 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not cap the CPU arm)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_leg(order, n_replicas, n_events, threads):
     """Time the oracle (CPU restatement; the reference itself needs GHC + LLVM 6 and cannot run here)."""
     import pyoracle as po
@@ -118,7 +126,7 @@ def run_reference(args, rank, world):
         return
     import pyoracle as po
 
-    threads = po.max_threads()
+    threads = host_threads()
     n_rep, n_ev = 2 * threads, args.ref_events
     vals = []
     for i in range(args.warmup + args.steps):
@@ -291,7 +299,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             import pyoracle as po
 
-            threads = po.max_threads()
+            threads = host_threads()
             n_cpu_rep = 2 * threads
             v, dt, tot, _ = cpu_leg(po.ORDER_FAST, n_cpu_rep, args.cpu_events, threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
