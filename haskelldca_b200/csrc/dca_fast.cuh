@@ -40,6 +40,9 @@ constexpr int EVW = 3;        // the event warp
 constexpr int NSLOT = 6;      // feature planes per agent lane group
 constexpr int SLOTP = 12;     // planes per slot = agent lane groups
 constexpr int WH = NROW * 4;  // floats per half of the weight array
+constexpr int NBLK = 22;      // queue blocks of 32 slots
+constexpr int QCAPS = NBLK * 32;  // 704 >= QCAP: whole blocks can be scanned
+static_assert(QCAPS >= QCAP, "queue blocks");
 
 struct Ev {  // an event and its candidate set (double-buffered: the event warp writes
              // the next one while the agents still use the current one)
@@ -55,11 +58,14 @@ struct alignas(16) SmemF {
   uint8_t x[WPAD];          // frep, [f][r][8]
   uint8_t cnt2[WPAD];       // users of ch within distance 2, [ch][r][8]
   uint32_t grid[NCELL][4];
-  double q_time[QCAP];
-  uint32_t q_id[QCAP];
+  double q_time[QCAPS];     // event queue slots: 0..48 NEW (one per cell), 49.. END; unused = +inf
+  uint32_t q_id[QCAPS];
   uint16_t q_key[QCAP];
   uint8_t q_hoff[QCAP];
-  long long stats[8];
+  double bm_t[NBLK];        // per block of 32 slots: its minimum (time, id) and where it is
+  uint32_t bm_id[NBLK];
+  uint16_t bm_s[NBLK];
+  uint16_t end_slot[NCELL][72];  // (cell, ch) -> slot of the END event of the call on ch at cell
   Ev ev[2];
   float P[72];              // plane sums of x.w (current state, current weights)
   float q[72];              // afterstate values of the candidates
@@ -69,7 +75,8 @@ struct alignas(16) SmemF {
 static_assert(sizeof(SmemF) % 16 == 0, "SmemF size");
 static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && offsetof(SmemF, grid) % 16 == 0 &&
               offsetof(SmemF, q_time) % 16 == 0 && offsetof(SmemF, q_id) % 16 == 0 && offsetof(SmemF, q_key) % 16 == 0 &&
-              offsetof(SmemF, q_hoff) % 8 == 0 && offsetof(SmemF, ev) % 8 == 0 && sizeof(Ev) % 8 == 0, "SmemF alignment");
+              offsetof(SmemF, q_hoff) % 8 == 0 && offsetof(SmemF, bm_t) % 8 == 0 && offsetof(SmemF, ev) % 8 == 0 &&
+              sizeof(Ev) % 8 == 0, "SmemF alignment");
 
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" ::: "memory"); }
 
@@ -77,15 +84,23 @@ __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" 
 // packed fp32 helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
-// bytes k, k+1 of v as floats: 0x4B0000bb is 2^23 + bb exactly
+// bytes k, k+1 of v as floats.  Default: I2F.U8 with a byte selector (XU pipe, which is otherwise
+// idle here).  DCA_CVT_PRMT: 0x4B0000bb is 2^23 + bb exactly, so PRMT + FADD2 does it on the ALU / FMA
+// pipes -- measured 9 % slower on B200 because those are the pipes the update needs.
 template <int K>
 __device__ __forceinline__ float2 cvt_pair(uint32_t v) {
+#ifndef DCA_CVT_PRMT
+  return make_float2((float)((v >> (8 * K)) & 0xFFu), (float)((v >> (8 * K + 8)) & 0xFFu));
+#endif
   float2 m = make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440 + K)),
                          __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440 + K + 1)));
   return __fadd2_rn(m, f2(-8388608.0f));
 }
 template <int K>
 __device__ __forceinline__ float cvt_one(uint32_t v) {
+#ifndef DCA_CVT_PRMT
+  return (float)((v >> (8 * K)) & 0xFFu);
+#endif
   return __fadd_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440 + K)), -8388608.0f);
 }
 struct Row7 {  // one row of the feature representation as floats
@@ -125,15 +140,29 @@ struct TdScalars {
 
 // Per-thread constants of an agent lane: where its rows live.
 struct Lane {
+  int vw;             // virtual warp (role) of this thread: 0..2 agent, 3 event
   int g8, r;          // lane group (0..11), row (0..7; 7 idles)
   int xoff, xoff5;    // byte offset of this lane's row in sm.x for slots 0-4 (+672*j) / slot 5
   int woff, woff5;    // float offset of this lane's row in a half of sm.w (+336*j) / slot 5
   bool rv, pv5;       // row valid; plane of slot 5 valid
 };
+// Roles could rotate over the hardware warps from CTA to CTA (hardware warp w runs on SM
+// sub-partition w % 4) to spread the lighter event warps over all four schedulers.  Measured on
+// B200: 15 % SLOWER than the fixed assignment (profiles/r1_v2_summary.md), so it is off.
+__device__ __forceinline__ int role_rotation() {
+#ifdef DCA_ROTATE_ROLES
+  return (int)((blockIdx.x * 2654435761u) >> 30);
+#else
+  return 0;
+#endif
+}
+__device__ __forceinline__ int virtual_tid() { return (int)((threadIdx.x + 32u * (unsigned)role_rotation()) & 127u); }
 __device__ __forceinline__ Lane make_lane() {
   Lane l;
-  l.g8 = threadIdx.x >> 3;
-  l.r = threadIdx.x & 7;
+  const int vt = virtual_tid();
+  l.vw = vt >> 5;
+  l.g8 = vt >> 3;
+  l.r = vt & 7;
   l.rv = l.r < 7;
   const int rc = l.rv ? l.r : 6;
   l.pv5 = SLOTP * (NSLOT - 1) + l.g8 <= NCH;
@@ -155,13 +184,17 @@ __device__ __forceinline__ Lane make_lane() {
 template <bool UPDATE>
 __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, const int act, const bool is_end,
                                            const TdScalars td, const uint2 n4b_r, const uint2 n2b_r) {
-  const int wid = warp_id();
+  const int wid = l.vw;
   // this lane's row of the N4 mask as floats; x' = x + sgn * mask on plane `act`
   Row7 dn4;
   const float sgn = is_end ? -1.0f : 1.0f;
   if (UPDATE) dn4 = cvt_row(n4b_r);
   float rs[NSLOT];
   float rg_acc = 0.0f;
+  // does this lane own a row of plane `act`?  (plane f lives on group f % 12 for f < 60, f - 60 above)
+  const bool own_act = UPDATE && act >= 0 && l.rv && l.g8 == (act >= SLOTP * (NSLOT - 1) ? act - SLOTP * (NSLOT - 1) : act % SLOTP);
+  uint2 xb_act = make_uint2(0, 0);
+  if (own_act) xb_act = *reinterpret_cast<const uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]);
 #pragma unroll
   for (int j = 0; j < NSLOT; ++j) {
     const bool last = j == NSLOT - 1;
@@ -184,7 +217,6 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
       xn.b = __ffma2_rn(f2(m), dn4.b, xo.b);
       xn.c = __ffma2_rn(f2(m), dn4.c, xo.c);
       xn.d = __fmaf_rn(m, dn4.d, xo.d);
-      if (isact && valid) *reinterpret_cast<uint2*>(&sm.x[xo_]) = is_end ? bsub(xb, n4b_r) : badd(xb, n4b_r);
       if (last && wid == 2 && act >= 0) {  // warp-uniform: the owners of plane 70 (n_elig) and of cnt2[act]
         if (f == NCH && pv) {
           const int co = act * PLANE + (l.rv ? l.r : 6) * ROWPAD;
@@ -227,6 +259,7 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     if (j == 0) rg_acc = l.rv ? rg : 0.0f;
     else if (valid) rg_acc = __fadd_rn(rg_acc, rg);
   }
+  if (own_act) *reinterpret_cast<uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]) = is_end ? bsub(xb_act, n4b_r) : badd(xb_act, n4b_r);
   // plane sums: xor-butterfly 1,2,4 over the 8 lanes of a group, the six slots interleaved
 #pragma unroll
   for (int s = 1; s < 8; s <<= 1) {
@@ -269,10 +302,10 @@ __device__ __forceinline__ VTree v_tree(const SmemF& sm) {
 // q[k] for every candidate: dense dot of afterstate k in the FAST tree, by
 // substituting the channel plane and the n_elig plane.  The 12 agent lane groups
 // take one candidate each per pass.
-__device__ __forceinline__ void q_eval(SmemF& sm, const Ev& ev, const VTree& vt, const int n, const bool is_end,
-                                       const uint2 n4b_r, const uint2 n2b_r) {
-  const int grp = threadIdx.x >> 3, r = threadIdx.x & 7;
-  const int wfirst = (threadIdx.x >> 5) * 4;  // first lane group of this warp
+__device__ __forceinline__ void q_eval(SmemF& sm, const Lane& l, const Ev& ev, const VTree& vt, const int n,
+                                       const bool is_end, const uint2 n4b_r, const uint2 n2b_r) {
+  const int grp = l.g8, r = l.r;
+  const int wfirst = l.vw * 4;  // first lane group of this warp
   if (wfirst >= n) return;  // warp-uniform: this warp has no candidate at all
   const bool rv = r < 7;
   const int rc = rv ? r : 6;
@@ -392,9 +425,7 @@ struct EvRegs {
   long long iter, n_events, loss_n;
   float loss_sum, min_loss;
   double mean_new, call_dur, call_dur_hoff, hoff_prob;
-  int ren_from, ren_to;                 // pending reassign (EventGen.hs:62-72) as q_key values; -1 = none
-  unsigned long long pt;                // pre-scan: min (time, id) over the stored queue
-  unsigned pid, pslot;
+  long long stats[8];                   // Stats counters (src/Stats.hs:15-30)
   unsigned long long dbase;             // cached draws: lane l holds draw dbase + l ...
   unsigned long long dword;             // ... its random word (per lane)
   double dnl;                           // ... and -log(u) of that word (per lane)
@@ -494,79 +525,82 @@ __device__ __forceinline__ void ev_candidates(const SmemF& sm, Ev& ev, const int
   __syncwarp();
 }
 
-// the pending re-key of `reassign` (EventGen.hs:62-72)
-__device__ __forceinline__ void ev_rename(SmemF& sm, EvRegs& e) {
-  if (e.ren_from < 0) return;
-  const unsigned total = QNEW + e.n_end;
-  const uint16_t want = (uint16_t)e.ren_from, to = (uint16_t)e.ren_to;
-#pragma unroll 2
-  for (unsigned i = QNEW + lane_id(); i < total; i += 32)
-    if (sm.q_key[i] == want) sm.q_key[i] = to;
-  e.ren_from = -1;
+// ---- the event queue (EventGen, src/EventGen/Internal.hs:44-53) as a dense slot table with
+// per-block minima: pop = argmin over (time, id) (EventGen.hs:39-50) costs one 22-wide reduction
+// plus the re-scan of the one or two 32-slot blocks it touched.
+struct QMin {
+  unsigned long long t;
+  unsigned id, lane;
+};
+// lexicographic warp argmin over (t, id); every lane gets the result and the winning lane
+__device__ __forceinline__ QMin warp_argmin(unsigned long long t, unsigned id) {
+  const unsigned hi = (unsigned)(t >> 32), lo = (unsigned)t;
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  bool ok = hi == mhi;
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, ok ? lo : 0xFFFFFFFFu);
+  ok = ok && lo == mlo;
+  const unsigned mid = __reduce_min_sync(0xffffffffu, ok ? id : 0xFFFFFFFFu);
+  ok = ok && id == mid;
+  QMin m;
+  m.t = ((unsigned long long)mhi << 32) | mlo;
+  m.id = mid;
+  m.lane = __ffs(__ballot_sync(0xffffffffu, ok)) - 1;
+  return m;
+}
+__device__ __forceinline__ void q_block_rescan(SmemF& sm, unsigned b) {
+  const int lane = lane_id();
+  const unsigned i = 32 * b + lane;
+  const QMin m = warp_argmin((unsigned long long)__double_as_longlong(sm.q_time[i]), sm.q_id[i]);
+  if (lane == 0) {
+    sm.bm_t[b] = __longlong_as_double((long long)m.t);
+    sm.bm_id[b] = m.id;
+    sm.bm_s[b] = (uint16_t)(32 * b + m.lane);
+  }
+}
+// a slot was just written with (t, id): lower its block's minimum if needed
+__device__ __forceinline__ void q_block_push(SmemF& sm, unsigned slot, unsigned long long t, unsigned id) {
+  __syncwarp();  // (an earlier push of this event may have lowered the same block)
+  const unsigned b = slot >> 5;
+  const unsigned long long bt = (unsigned long long)__double_as_longlong(sm.bm_t[b]);
+  const unsigned bid = sm.bm_id[b];
+  if (lane_id() == 0 && (t < bt || (t == bt && id < bid))) {
+    sm.bm_t[b] = __longlong_as_double((long long)t);
+    sm.bm_id[b] = id;
+    sm.bm_s[b] = (uint16_t)slot;
+  }
+}
+// slot of the earliest stored event
+__device__ __forceinline__ unsigned q_min_slot(const SmemF& sm) {
+  const int lane = lane_id();
+  unsigned long long t = 0xFFFFFFFFFFFFFFFFULL;
+  unsigned id = 0xFFFFFFFFu;
+  if (lane < NBLK) {
+    t = (unsigned long long)__double_as_longlong(sm.bm_t[lane]);
+    id = sm.bm_id[lane];
+  }
+  const QMin m = warp_argmin(t, id);
+  return sm.bm_s[m.lane];
+}
+// everything derived from the slot table (run once per launch by the event warp)
+__device__ __forceinline__ void q_build(SmemF& sm, unsigned n_end) {
+  const int lane = lane_id();
+  for (unsigned i = QNEW + n_end + lane; i < QCAPS; i += 32) {  // unused slots never win
+    sm.q_time[i] = CUDART_INF;
+    sm.q_id[i] = 0xFFFFFFFFu;
+  }
+  for (unsigned i = QNEW + lane; i < QNEW + n_end; i += 32) {
+    const unsigned key = sm.q_key[i];
+    sm.end_slot[key >> 7][key & 127u] = (uint16_t)i;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (unsigned b = 0; b < NBLK; ++b) q_block_rescan(sm, b);
   __syncwarp();
 }
 
-__device__ __noinline__ void ev_prescan_exact(const double* q_time, const uint32_t* q_id, unsigned total,
-                                              unsigned long long tmin, unsigned* bslot_out, unsigned* mid_out,
-                                              unsigned* src_out) {
-  const int lane = lane_id();
-  unsigned long long bt = 0xFFFFFFFFFFFFFFFFULL;
-  unsigned bid = 0xFFFFFFFFu, bslot = 0xFFFFFFFFu;
-#pragma unroll 1
-  for (unsigned i = lane; i < total; i += 32) {
-    const unsigned long long t = (unsigned long long)__double_as_longlong(q_time[i]);
-    const unsigned id = q_id[i];
-    if (t < bt || (t == bt && id < bid)) { bt = t; bid = id; bslot = i; }
-  }
-  bool ok = bt == tmin;
-  const unsigned mid = __reduce_min_sync(0xffffffffu, ok ? bid : 0xFFFFFFFFu);
-  ok = ok && (bid == mid);
-  *bslot_out = bslot;
-  *mid_out = mid;
-  *src_out = __ffs(__ballot_sync(0xffffffffu, ok)) - 1;
-}
-
-// pre-scan of the stored queue: argmin over (time, id) (pop, EventGen.hs:39-50)
-__device__ __forceinline__ void ev_prescan(SmemF& sm, EvRegs& e) {
-  ev_rename(sm, e);
-  const unsigned total = QNEW + e.n_end;
-  const int lane = lane_id();
-  unsigned long long bt = 0xFFFFFFFFFFFFFFFFULL;
-  unsigned bslot = 0xFFFFFFFFu;
-  bool tie = false;
-#pragma unroll 4
-  for (unsigned i = lane; i < total; i += 32) {
-    const unsigned long long t = (unsigned long long)__double_as_longlong(sm.q_time[i]);
-    tie |= (t == bt);
-    if (t < bt) { bt = t; bslot = i; }
-  }
-  const unsigned hi = (unsigned)(bt >> 32), lo = (unsigned)bt;
-  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-  bool ok = (hi == mhi);
-  const unsigned mlo = __reduce_min_sync(0xffffffffu, ok ? lo : 0xFFFFFFFFu);
-  ok = ok && (lo == mlo);
-  const unsigned okm = __ballot_sync(0xffffffffu, ok);
-  unsigned mid, src;
-  if (__any_sync(0xffffffffu, tie) || (okm & (okm - 1))) {
-    // equal times somewhere (practically never): redo the scan on (time, id) exactly
-    ev_prescan_exact(sm.q_time, sm.q_id, total, ((unsigned long long)mhi << 32) | mlo, &bslot, &mid, &src);
-  } else {
-    src = __ffs(okm) - 1;
-    mid = sm.q_id[__shfl_sync(0xffffffffu, bslot, src)];
-  }
-  e.pt = ((unsigned long long)mhi << 32) | mlo;
-  e.pid = mid;
-  e.pslot = __shfl_sync(0xffffffffu, bslot, src);
-}
-
-// what the event warp does for event `ev` while the agents evaluate its candidates:
-// queue pre-scan (unless the next event is already known) and random draws
+// random draws of the event are prepared while the agents evaluate its candidates
 __device__ __forceinline__ void ev_prepare(SmemF& sm, EvRegs& e, const Ev& ev) {
-  const int type = ev.type;
-  const bool pops = !(type == EV_END && ev.hoff != HOFF_NONE);
-  if (pops) ev_prescan(sm, e);
-  else ev_rename(sm, e);
-  if (type != EV_END) ev_draws(e);
+  if (ev.type != EV_END) ev_draws(e);
 }
 
 // environmentStep (Simulator.hs:101-134) for the event (type, cell, ev_ch,
@@ -575,31 +609,28 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx
                                                     const int ev_ch, const int ev_hoff, const double time,
                                                     const int act) {
   const int lane = lane_id();
-  if (lane == 0) {
-    // Stats hooks, Stats.hs:61-81 as called from Simulator.hs:105-114
-    if (type == EV_NEW) {
-      sm.stats[6]++; sm.stats[0]++;
-      if (act >= 0) sm.stats[1]++;
-      else { sm.stats[2]++; sm.stats[7]++; }
-    } else if (type == EV_HOFF) {
-      sm.stats[3]++;
-      if (act < 0) { sm.stats[2]++; sm.stats[7]++; }  // Simulator.hs:113
-    } else {
-      sm.stats[4]++;
-    }
-    if (act >= 0) sm.grid[cell][act >> 5] ^= 1u << (act & 31);  // executeAction, Gridfuncs.hs:105-110
+  // Stats hooks, Stats.hs:61-81 as called from Simulator.hs:105-114
+  if (type == EV_NEW) {
+    e.stats[6]++; e.stats[0]++;
+    if (act >= 0) e.stats[1]++;
+    else { e.stats[2]++; e.stats[7]++; }
+  } else if (type == EV_HOFF) {
+    e.stats[3]++;
+    if (act < 0) { e.stats[2]++; e.stats[7]++; }  // Simulator.hs:113
+  } else {
+    e.stats[4]++;
   }
-  bool have_new = false, have_end = false;
-  unsigned long long t_new = 0, t_end = 0;
-  unsigned id_new = 0, id_end = 0;
+  if (lane == 0 && act >= 0) sm.grid[cell][act >> 5] ^= 1u << (act & 31);  // executeAction, Gridfuncs.hs:105-110
+  bool have_end = false;
+  unsigned long long t_end = 0;
+  unsigned id_end = 0;
   int end_hoff = HOFF_NONE;
   if (type == EV_NEW) {
     // generateNewEvent, EventGen.hs:75-85: always, at time + Exp(mean_new)
     const double tn = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 0), e.mean_new));
-    t_new = (unsigned long long)__double_as_longlong(tn);
-    id_new = e.next_id++;
-    have_new = true;
+    const unsigned id_new = e.next_id++;
     if (lane == 0) { sm.q_time[cell] = tn; sm.q_id[cell] = id_new; }
+    q_block_push(sm, (unsigned)cell, (unsigned long long)__double_as_longlong(tn), id_new);
     unsigned used = 1;
     if (act >= 0) {
       const unsigned long long w1 = ev_draw_word(e, 1);
@@ -633,17 +664,26 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx
       have_end = true;
       e.ndraws += 1;
     }
-  } else if (act >= 0 && act != ev_ch) {  // END toCh, Simulator.hs:129-130: reassign cell act -> ev_ch
-    e.ren_from = (cell << 7) | act;
-    e.ren_to = (cell << 7) | ev_ch;
+  } else if (act >= 0 && act != ev_ch) {
+    // END toCh, Simulator.hs:129-130: reassign cell act -> ev_ch (EventGen.hs:62-72): the call that
+    // used `act` continues on ev_ch, so its END event is re-keyed
+    if (lane == 0) {
+      const unsigned sl = sm.end_slot[cell][act];
+      sm.q_key[sl] = (uint16_t)((cell << 7) | ev_ch);
+      sm.end_slot[cell][ev_ch] = (uint16_t)sl;
+    }
   }
   if (have_end) {  // push END (cell, act) [hoff] at slot QNEW + n_end
     const unsigned slot = QNEW + e.n_end;
-    if (lane == 0 && slot < QCAP) {
-      sm.q_time[slot] = __longlong_as_double((long long)t_end);
-      sm.q_id[slot] = id_end;
-      sm.q_key[slot] = (uint16_t)((cell << 7) | act);
-      sm.q_hoff[slot] = (uint8_t)end_hoff;
+    if (slot < QCAP) {
+      if (lane == 0) {
+        sm.q_time[slot] = __longlong_as_double((long long)t_end);
+        sm.q_id[slot] = id_end;
+        sm.q_key[slot] = (uint16_t)((cell << 7) | act);
+        sm.q_hoff[slot] = (uint8_t)end_hoff;
+        sm.end_slot[cell][act] = (uint16_t)slot;
+      }
+      q_block_push(sm, slot, t_end, id_end);
     }
     e.n_end++;
   }
@@ -654,36 +694,37 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx
   if (type == EV_END && ev_hoff != HOFF_NONE) {
     // the HOFF that follows a hand-off END: same time, next id (EventGen.hs:107-108)
     nx_time = time; nx_type = EV_HOFF; nx_cell = ev_hoff;
-  } else {
-    // min over (pre-scan, pushed NEW, pushed END) by (time, id)
-    unsigned long long bt = e.pt;
-    unsigned bid = e.pid;
-    int src = 0;
-    if (have_new && (t_new < bt || (t_new == bt && id_new < bid))) { bt = t_new; bid = id_new; src = 1; }
-    if (have_end && (t_end < bt || (t_end == bt && id_end < bid))) { bt = t_end; bid = id_end; src = 2; }
-    nx_time = __longlong_as_double((long long)bt);
-    if (src == 2) {  // the END just pushed sits in the last slot: drop it again
-      nx_type = EV_END; nx_cell = cell; nx_ch = act; nx_hoff = end_hoff;
-      e.n_end--;
+  } else {  // pop, EventGen.hs:39-50
+    const unsigned slot = q_min_slot(sm);
+    nx_time = sm.q_time[slot];
+    if (slot < QNEW) {
+      nx_type = EV_NEW; nx_cell = (int)slot;
+      __syncwarp();
+      if (lane == 0) { sm.q_time[slot] = CUDART_INF; sm.q_id[slot] = 0xFFFFFFFFu; }
+      __syncwarp();
+      q_block_rescan(sm, slot >> 5);
     } else {
-      const unsigned slot = src == 1 ? (unsigned)cell : e.pslot;
-      if (slot < QNEW) {
-        nx_type = EV_NEW; nx_cell = (int)slot;
-        if (lane == 0) sm.q_time[slot] = CUDART_INF;
-      } else {
-        int key = sm.q_key[slot];
-        if (key == e.ren_from) key = e.ren_to;  // re-keyed by this very event, not yet written
-        nx_type = EV_END; nx_cell = key >> 7; nx_ch = key & 127; nx_hoff = sm.q_hoff[slot];
-        const unsigned last = QNEW + e.n_end - 1;
-        __syncwarp();
-        if (lane == 0 && slot != last) {
+      const int key = sm.q_key[slot];
+      nx_type = EV_END; nx_cell = key >> 7; nx_ch = key & 127; nx_hoff = sm.q_hoff[slot];
+      const unsigned last = QNEW + e.n_end - 1;
+      const bool last_was_min = sm.bm_s[last >> 5] == last;
+      __syncwarp();
+      if (lane == 0) {
+        if (slot != last) {  // keep the table dense: the last END event moves into the hole
+          const unsigned lkey = sm.q_key[last];
           sm.q_time[slot] = sm.q_time[last];
           sm.q_id[slot] = sm.q_id[last];
-          sm.q_key[slot] = sm.q_key[last];
+          sm.q_key[slot] = (uint16_t)lkey;
           sm.q_hoff[slot] = sm.q_hoff[last];
+          sm.end_slot[lkey >> 7][lkey & 127u] = (uint16_t)slot;
         }
-        e.n_end--;
+        sm.q_time[last] = CUDART_INF;
+        sm.q_id[last] = 0xFFFFFFFFu;
       }
+      e.n_end--;
+      __syncwarp();
+      q_block_rescan(sm, slot >> 5);
+      if ((last >> 5) != (slot >> 5) && last_was_min) q_block_rescan(sm, last >> 5);
     }
   }
   if (lane == 0) {
@@ -772,11 +813,10 @@ __device__ __forceinline__ void stage_in(SmemF& sm, const RepState* g) {
   copy8(sm.x, g->x, sizeof sm.x);
   copy8(sm.cnt2, g->cnt2, sizeof sm.cnt2);
   copy16(sm.grid, g->grid, sizeof sm.grid);
-  copy16(sm.q_time, g->q_time, sizeof sm.q_time);
-  copy16(sm.q_id, g->q_id, sizeof sm.q_id);
+  copy16(sm.q_time, g->q_time, sizeof g->q_time);
+  copy16(sm.q_id, g->q_id, sizeof g->q_id);
   copy16(sm.q_key, g->q_key, sizeof sm.q_key);
   copy8(sm.q_hoff, g->q_hoff, sizeof sm.q_hoff);
-  if (threadIdx.x < 8) sm.stats[threadIdx.x] = g->stats[threadIdx.x];
   if (threadIdx.x == 0) {
     Ev& ev = sm.ev[0];
     ev.time = g->ev_time; ev.type = g->ev_type; ev.cell = g->ev_cell; ev.ch = g->ev_ch; ev.hoff = g->ev_hoff;
@@ -795,11 +835,10 @@ __device__ __forceinline__ void stage_out(const SmemF& sm, RepState* g) {
   copy8(g->x, sm.x, sizeof sm.x);
   copy8(g->cnt2, sm.cnt2, sizeof sm.cnt2);
   copy16(g->grid, sm.grid, sizeof sm.grid);
-  copy16(g->q_time, sm.q_time, sizeof sm.q_time);
-  copy16(g->q_id, sm.q_id, sizeof sm.q_id);
+  copy16(g->q_time, sm.q_time, sizeof g->q_time);
+  copy16(g->q_id, sm.q_id, sizeof g->q_id);
   copy16(g->q_key, sm.q_key, sizeof sm.q_key);
   copy8(g->q_hoff, sm.q_hoff, sizeof sm.q_hoff);
-  if (threadIdx.x < 8) g->stats[threadIdx.x] = sm.stats[threadIdx.x];
 }
 // wGradCorr rows of an agent lane
 __device__ __forceinline__ void load_wg(Agent& ag, const RepState* g, const Lane& l) {
@@ -834,8 +873,8 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
   e.iter = g->iter; e.n_events = g->n_events; e.loss_n = g->loss_n;
   e.loss_sum = g->loss_sum; e.min_loss = g->min_loss;
   e.mean_new = g->mean_new; e.call_dur = g->call_dur; e.call_dur_hoff = g->call_dur_hoff; e.hoff_prob = g->hoff_prob;
-  e.ren_from = -1; e.ren_to = -1;
-  e.pt = 0xFFFFFFFFFFFFFFFFULL; e.pid = 0xFFFFFFFFu; e.pslot = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) e.stats[k] = g->stats[k];
   e.dbase = 0xFFFFFFFFFFFFFFF0ULL; e.dword = 0; e.dnl = 0.0;  // (empty draw cache)
   e.rng_mode = a.rng_mode; e.k0 = a.key0; e.k1 = a.key1; e.stream = g->stream;
   e.tape_w = nullptr; e.tape_l = nullptr; e.tape_len = 0;
@@ -876,7 +915,7 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
     // accFn1 = getAction (Simulator.hs:154-172)
     const VTree vt = v_tree(sm);
-    if (n > 0) q_eval(sm, ev, vt, n, is_end, n4b_r, n2b_r);
+    if (n > 0) q_eval(sm, l, ev, vt, n, is_end, n4b_r, n2b_r);
     cta_barrier();  // B2
     const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
@@ -885,10 +924,10 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     cta_barrier();  // B1
     if (sm.status != ST_RUNNING) break;  // uniform
   }
-  cta_barrier();  // (the event warp flushes a pending re-key before the queue is copied out)
+  cta_barrier();
   stage_out(sm, g);
   store_wg(ag, g, l);
-  if (threadIdx.x == 0) {
+  if (l.vw == 0 && lane_id() == 0) {
     g->avg_reward = avgR;
     g->ncalls = ncalls;
   }
@@ -905,6 +944,7 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   EvRegs e;
   ev_load(e, a, g, rep);
   cta_barrier();
+  q_build(sm, e.n_end);
   ev_candidates(sm, sm.ev[0], -1);
   cta_barrier();  // B1
   long long it = 0;
@@ -963,11 +1003,12 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     cta_barrier();  // B1
     if (stop != ST_RUNNING) { ++it; break; }
   }
-  ev_rename(sm, e);
   cta_barrier();
   stage_out(sm, g);
   if (lane == 0) {
     const Ev& ev = sm.ev[it & 1];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g->stats[k] = e.stats[k];
     g->n_end = e.n_end; g->next_id = e.next_id; g->ndraws = e.ndraws;
     g->iter = e.iter; g->loss_n = e.loss_n; g->loss_sum = e.loss_sum;
     g->ev_time = ev.time; g->ev_type = ev.type; g->ev_cell = ev.cell; g->ev_ch = ev.ch; g->ev_hoff = ev.hoff;
@@ -986,7 +1027,7 @@ __global__ void __launch_bounds__(NT, DCA_MIN_CTAS) k_run_fast(RunArgs a) {
   if (rep >= a.n_replicas) return;
   RepState* g = a.states + rep;
   if (!g->initialized || g->status != ST_RUNNING) return;  // uniform
-  if (warp_id() == EVW) event_main<TRACE>(sm, a, g, rep);
+  if ((virtual_tid() >> 5) == EVW) event_main<TRACE>(sm, a, g, rep);
   else agent_main<TRACE>(sm, a, g);
 }
 
@@ -1002,8 +1043,8 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
   RepState* g = states + rep;
   const bool is_end = is_end_i != 0;
-  const int wid = warp_id(), lane = lane_id();
   const Lane l = make_lane();
+  const int wid = l.vw, lane = lane_id();
   const int rc = l.rv ? l.r : 6;
   Agent ag;
   stage_in(sm, g);
@@ -1027,7 +1068,7 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   const int n = ev.ncand;
   const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
   const VTree vt = v_tree(sm);
-  if (n > 0 && wid != EVW) q_eval(sm, ev, vt, n, is_end, n4b_r, n2b_r);
+  if (n > 0 && wid != EVW) q_eval(sm, l, ev, vt, n, is_end, n4b_r, n2b_r);
   __syncthreads();
   if (mode == 0) {
     float qb;
