@@ -84,12 +84,12 @@ __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" 
 // packed fp32 helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
-// bytes k, k+1 of v as floats.  Default: I2F.U8 with a byte selector (XU pipe, which is otherwise
-// idle here).  DCA_CVT_PRMT: 0x4B0000bb is 2^23 + bb exactly, so PRMT + FADD2 does it on the ALU / FMA
-// pipes -- measured 9 % slower on B200 because those are the pipes the update needs.
+// bytes k, k+1 of v as floats: 0x4B0000bb is 2^23 + bb exactly, so PRMT + FADD2 converts on the
+// ALU / FMA pipes.  DCA_CVT_I2F: I2F.U8 with a byte selector on the XU pipe instead (fewer
+// instructions, longer latency) -- measured 2-7 % slower on B200.
 template <int K>
 __device__ __forceinline__ float2 cvt_pair(uint32_t v) {
-#ifndef DCA_CVT_PRMT
+#ifdef DCA_CVT_I2F
   return make_float2((float)((v >> (8 * K)) & 0xFFu), (float)((v >> (8 * K + 8)) & 0xFFu));
 #endif
   float2 m = make_float2(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440 + K)),
@@ -98,7 +98,7 @@ __device__ __forceinline__ float2 cvt_pair(uint32_t v) {
 }
 template <int K>
 __device__ __forceinline__ float cvt_one(uint32_t v) {
-#ifndef DCA_CVT_PRMT
+#ifdef DCA_CVT_I2F
   return (float)((v >> (8 * K)) & 0xFFu);
 #endif
   return __fadd_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440 + K)), -8388608.0f);
@@ -1016,8 +1016,10 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   }
 }
 
+// 4 CTAs per SM (128 registers/thread, no spills) beat 5 (96 registers, spills and rematerialised
+// lane constants in the agent loop): 236 vs 206 M events/s on B200.
 #ifndef DCA_MIN_CTAS
-#define DCA_MIN_CTAS 5
+#define DCA_MIN_CTAS 4
 #endif
 template <bool TRACE>
 __global__ void __launch_bounds__(NT, DCA_MIN_CTAS) k_run_fast(RunArgs a) {
