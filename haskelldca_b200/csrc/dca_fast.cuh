@@ -70,7 +70,8 @@ struct alignas(16) SmemF {
   float P[72];              // plane sums of x.w (current state, current weights)
   float q[72];              // afterstate values of the candidates
   float Wg[4];              // per-warp partial sums of x.wGradCorr
-  int status, pad0, pad1, pad2;
+  float alpha_net, alpha_avg, alpha_grad;  // alphaNet, alphaAvg, alphaGrad of this replica
+  int status;
 };
 static_assert(sizeof(SmemF) % 16 == 0, "SmemF size");
 static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && offsetof(SmemF, grid) % 16 == 0 &&
@@ -142,9 +143,9 @@ struct TdScalars {
 struct Lane {
   int vw;             // virtual warp (role) of this thread: 0..2 agent, 3 event
   int g8, r;          // lane group (0..11), row (0..7; 7 idles)
-  int xoff, xoff5;    // byte offset of this lane's row in sm.x for slots 0-4 (+672*j) / slot 5
-  int woff, woff5;    // float offset of this lane's row in a half of sm.w (+336*j) / slot 5
-  bool rv, pv5;       // row valid; plane of slot 5 valid
+  int xoff;           // byte offset of this lane's row in sm.x for slot 0 (+672 per slot)
+  int woff;           // float offset of this lane's row in a half of sm.w for slot 0 (+336 per slot)
+  bool rv;            // row valid
 };
 // Roles could rotate over the hardware warps from CTA to CTA (hardware warp w runs on SM
 // sub-partition w % 4) to spread the lighter event warps over all four schedulers.  Measured on
@@ -165,12 +166,8 @@ __device__ __forceinline__ Lane make_lane() {
   l.r = vt & 7;
   l.rv = l.r < 7;
   const int rc = l.rv ? l.r : 6;
-  l.pv5 = SLOTP * (NSLOT - 1) + l.g8 <= NCH;
-  const int f5 = l.pv5 ? SLOTP * (NSLOT - 1) + l.g8 : NCH;
   l.xoff = l.g8 * PLANE + rc * ROWPAD;
-  l.xoff5 = f5 * PLANE + rc * ROWPAD;
   l.woff = (l.g8 * 7 + rc) * 4;
-  l.woff5 = (f5 * 7 + rc) * 4;
   return l;
 }
 
@@ -185,10 +182,12 @@ template <bool UPDATE>
 __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, const int act, const bool is_end,
                                            const TdScalars td, const uint2 n4b_r, const uint2 n2b_r) {
   const int wid = l.vw;
-  // this lane's row of the N4 mask as floats; x' = x + sgn * mask on plane `act`
-  Row7 dn4;
-  const float sgn = is_end ? -1.0f : 1.0f;
-  if (UPDATE) dn4 = cvt_row(n4b_r);
+  // the warp-slot that holds plane `act` (warp-uniform)
+  int ja = -1, wact = -1;
+  if (UPDATE && act >= 0) {
+    ja = act >= SLOTP * (NSLOT - 1) ? NSLOT - 1 : act / SLOTP;
+    wact = (act - SLOTP * ja) >> 2;
+  }
   float rs[NSLOT];
   float rg_acc = 0.0f;
   // does this lane own a row of plane `act`?  (plane f lives on group f % 12 for f < 60, f - 60 above)
@@ -198,11 +197,12 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
 #pragma unroll
   for (int j = 0; j < NSLOT; ++j) {
     const bool last = j == NSLOT - 1;
-    const int f = last ? (l.pv5 ? SLOTP * j + l.g8 : NCH) : SLOTP * j + l.g8;
-    const bool pv = last ? l.pv5 : true;
+    // slot 5 holds planes 60..70 on groups 0..10; group 11 has no plane there and shadows plane 70
+    const bool pv = last ? l.g8 != SLOTP - 1 : true;
+    const int f = SLOTP * j + l.g8 - (pv ? 0 : 1);
     const bool valid = pv && l.rv;
-    const int xo_ = last ? l.xoff5 : l.xoff + j * SLOTP * PLANE;
-    const int wo_ = last ? l.woff5 : l.woff + j * SLOTP * 28;
+    const int xo_ = l.xoff + j * SLOTP * PLANE - (pv ? 0 : PLANE);
+    const int wo_ = l.woff + j * SLOTP * 28 - (pv ? 0 : 28);
     const uint2 xb = *reinterpret_cast<const uint2*>(&sm.x[xo_]);
     const float4 wa = *reinterpret_cast<const float4*>(&sm.w[0][wo_]);
     const float4 wb = *reinterpret_cast<const float4*>(&sm.w[1][wo_]);
@@ -211,12 +211,9 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     const Row7 xo = cvt_row(xb);
     Row7 xn = xo;
     if (UPDATE) {
-      const bool isact = f == act;  // (act = -1 matches nothing)
-      const float m = isact ? sgn : 0.0f;
-      xn.a = __ffma2_rn(f2(m), dn4.a, xo.a);
-      xn.b = __ffma2_rn(f2(m), dn4.b, xo.b);
-      xn.c = __ffma2_rn(f2(m), dn4.c, xo.c);
-      xn.d = __fmaf_rn(m, dn4.d, xo.d);
+      if (j == ja && wid == wact) {  // warp-uniform: this warp's slot j holds plane `act`
+        if (f == act) xn = cvt_row(is_end ? bsub(xb, n4b_r) : badd(xb, n4b_r));
+      }
       if (last && wid == 2 && act >= 0) {  // warp-uniform: the owners of plane 70 (n_elig) and of cnt2[act]
         if (f == NCH && pv) {
           const int co = act * PLANE + (l.rv ? l.r : 6) * ROWPAD;
@@ -269,7 +266,7 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
   if (l.r == 0) {
 #pragma unroll
     for (int j = 0; j < NSLOT; ++j)
-      if (j < NSLOT - 1 || l.pv5) sm.P[SLOTP * j + l.g8] = rs[j];
+      if (j < NSLOT - 1 || l.g8 != SLOTP - 1) sm.P[SLOTP * j + l.g8] = rs[j];
   }
   // warp sum of x.wg: xor-butterfly 1,2,4,8,16
 #pragma unroll
@@ -394,8 +391,8 @@ struct Decision {
   TdScalars td;
 };
 __device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const VTree& vt, int n, bool is_end,
-                                           float& avgR, int& ncalls, float alpha_net, float alpha_avg,
-                                           float alpha_grad) {
+                                           float& avgR, int& ncalls) {
+  const float alpha_net = sm.alpha_net, alpha_avg = sm.alpha_avg, alpha_grad = sm.alpha_grad;
   Decision d;
   d.act = -1;
   float next_val = vt.val;  // no action: nextFrep = frep (Simulator.hs:170-171)
@@ -822,6 +819,7 @@ __device__ __forceinline__ void stage_in(SmemF& sm, const RepState* g) {
     ev.time = g->ev_time; ev.type = g->ev_type; ev.cell = g->ev_cell; ev.ch = g->ev_ch; ev.hoff = g->ev_hoff;
     ev.ncand = 0;
     sm.status = g->status;
+    sm.alpha_net = g->alpha_net; sm.alpha_avg = g->alpha_avg; sm.alpha_grad = g->alpha_grad;
   }
 }
 __device__ __forceinline__ void stage_out(const SmemF& sm, RepState* g) {
@@ -903,7 +901,6 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
   load_wg(ag, g, l);
   float avgR = g->avg_reward;
   int ncalls = g->ncalls;
-  const float alpha_net = g->alpha_net, alpha_avg = g->alpha_avg, alpha_grad = g->alpha_grad;
   cta_barrier();
   dense_pass<false>(sm, ag, l, -1, false, TdScalars{0.f, 0.f, 0.f, 0.f}, make_uint2(0, 0), make_uint2(0, 0));
   cta_barrier();  // B1
@@ -917,7 +914,7 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const VTree vt = v_tree(sm);
     if (n > 0) q_eval(sm, l, ev, vt, n, is_end, n4b_r, n2b_r);
     cta_barrier();  // B2
-    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
+    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
     dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
     if (sync_end) cta_barrier();
@@ -940,7 +937,6 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   stage_in(sm, g);
   float avgR = g->avg_reward;
   int ncalls = g->ncalls;
-  const float alpha_net = g->alpha_net, alpha_avg = g->alpha_avg, alpha_grad = g->alpha_grad;
   EvRegs e;
   ev_load(e, a, g, rep);
   cta_barrier();
@@ -959,7 +955,7 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const VTree vt = v_tree(sm);
     ev_prepare(sm, e, ev);
     cta_barrier();  // B2
-    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
+    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
     ev_environment_step(sm, e, nx, type, cell, ev_ch, ev_hoff, time, d.act);  // Simulator.hs:101-134
     ev_candidates(sm, nx, d.act);
     e.iter += 1;  // Simulator.hs:131
@@ -1054,6 +1050,7 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   float avgR = g->avg_reward;
   int ncalls = g->ncalls;
   __syncthreads();
+  if (threadIdx.x == 0) { sm.alpha_net = alpha_net; sm.alpha_avg = alpha_avg; sm.alpha_grad = alpha_grad; }
   Ev& ev = sm.ev[0];
   if (wid == EVW) {
     if (lane == 0) { ev.cell = cell; ev.type = is_end ? EV_END : EV_NEW; }
@@ -1078,7 +1075,7 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
     if (threadIdx.x == 0) out->ch = act;
     return;
   }
-  const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, alpha_net, alpha_avg, alpha_grad);
+  const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
   if (wid == EVW) {
     if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);
   } else {
