@@ -98,6 +98,9 @@ SYMBOLS = {
                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "dca_dense_dot": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),
+    "dca_checkpoint_size": (C.c_size_t, [C.c_void_p]),
+    "dca_checkpoint_save": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "dca_checkpoint_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "dca_read_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(Event)]),
     "dca_write_state": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]),

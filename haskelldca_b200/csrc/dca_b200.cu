@@ -585,6 +585,49 @@ int dca_write_state(dca_handle* h, int32_t replica, const uint8_t* grid, const f
   return DCA_OK;
 }
 
+// ---- checkpoint / resume: the replica blobs verbatim behind a small header ----------
+namespace {
+struct CkptHeader {
+  uint64_t magic;      // "DCAB200\1"
+  uint32_t blob_bytes; // sizeof(RepState)
+  int32_t n_replicas;
+  int32_t order, rng_mode;
+  uint64_t reserved;
+};
+constexpr uint64_t kCkptMagic = 0x0130303242414344ULL;
+}  // namespace
+
+size_t dca_checkpoint_size(const dca_handle* h) {
+  return h ? sizeof(CkptHeader) + sizeof(RepState) * (size_t)h->n : 0;
+}
+
+int dca_checkpoint_save(dca_handle* h, void* buf, size_t size) {
+  if (!h || !buf || size < dca_checkpoint_size(h)) return fail(h, DCA_ERR_ARG, "dca_checkpoint_save: bad argument");
+  CK(cudaSetDevice(h->device));
+  CkptHeader hd{kCkptMagic, (uint32_t)sizeof(RepState), h->n, h->cfg.order, h->cfg.rng_mode, 0};
+  memcpy(buf, &hd, sizeof hd);
+  CK(cudaMemcpyAsync(static_cast<char*>(buf) + sizeof hd, h->d_states, sizeof(RepState) * (size_t)h->n,
+                     cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DCA_OK;
+}
+
+int dca_checkpoint_load(dca_handle* h, const void* buf, size_t size) {
+  if (!h || !buf || size < dca_checkpoint_size(h)) return fail(h, DCA_ERR_ARG, "dca_checkpoint_load: bad argument");
+  CkptHeader hd;
+  memcpy(&hd, buf, sizeof hd);
+  if (hd.magic != kCkptMagic || hd.blob_bytes != sizeof(RepState) || hd.n_replicas != h->n ||
+      hd.order != h->cfg.order || hd.rng_mode != h->cfg.rng_mode)
+    return fail(h, DCA_ERR_STATE, "dca_checkpoint_load: the blob does not match this handle (replicas, order, rng mode or layout)");
+  CK(cudaSetDevice(h->device));
+  int rc = sync_tapes(h);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->d_states, static_cast<const char*>(buf) + sizeof hd, sizeof(RepState) * (size_t)h->n,
+                     cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DCA_OK;
+}
+
 static int fetch_summary(dca_handle* h, std::vector<Summary>& out) {
   CK(cudaSetDevice(h->device));
   k_summary<<<(h->n + 127) / 128, 128, 0, h->stream>>>(h->d_states, h->n, h->d_summary);

@@ -147,14 +147,16 @@ struct Lane {
   int woff;           // float offset of this lane's row in a half of sm.w for slot 0 (+336 per slot)
   bool rv;            // row valid
 };
-// Roles could rotate over the hardware warps from CTA to CTA (hardware warp w runs on SM
-// sub-partition w % 4) to spread the lighter event warps over all four schedulers.  Measured on
-// B200: 15 % SLOWER than the fixed assignment (profiles/r1_v2_summary.md), so it is off.
+// Roles rotate over the hardware warps from CTA to CTA (hardware warp w runs on SM sub-partition
+// w % 4): co-resident CTAs (block ids b, b + #SMs, b + 2 #SMs, ... in the first wave) then place their
+// light event warps on four different schedulers instead of all on the same one.
 __device__ __forceinline__ int role_rotation() {
-#ifdef DCA_ROTATE_ROLES
-  return (int)((blockIdx.x * 2654435761u) >> 30);
-#else
+#ifdef DCA_NO_ROTATE_ROLES
   return 0;
+#else
+  unsigned nsm;
+  asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+  return (int)((blockIdx.x / nsm) & 3u);
 #endif
 }
 __device__ __forceinline__ int virtual_tid() { return (int)((threadIdx.x + 32u * (unsigned)role_rotation()) & 127u); }

@@ -145,6 +145,18 @@ class Replicas:
             int(is_end), cell[0], cell[1], int(ch), C.byref(loss), C.byref(isnan), C.byref(reward)), self.h)
         return np.float32(loss.value), bool(isnan.value), reward.value
 
+    # ---- checkpoint / resume ----------------------------------------------------------
+    def checkpoint(self) -> np.ndarray:
+        """the complete state of every replica as one opaque uint8 blob"""
+        L = _ffi.load()
+        buf = np.empty(L.dca_checkpoint_size(self.h), dtype=np.uint8)
+        _ffi.check(L.dca_checkpoint_save(self.h, _ffi.ptr(buf), buf.nbytes), self.h)
+        return buf
+
+    def restore(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        _ffi.check(_ffi.load().dca_checkpoint_load(self.h, _ffi.ptr(blob), blob.nbytes), self.h)
+
     # ---- read-back ---------------------------------------------------------------
     def read_state(self, replica=0):
         grid = np.zeros((ROWS, COLS, CHANNELS), dtype=np.uint8)

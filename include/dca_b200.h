@@ -226,6 +226,14 @@ int dca_sum_stats(dca_handle *h, int64_t out[10], void **dev_ptr);
 /* Stats.hs:83-92 */
 void dca_stats_cumus(const int64_t stats[DCA_N_STATS], double out3[3]);
 
+/* ---- checkpoint / resume (absent in the reference) ------------------ */
+/* The complete simulator state of every replica (grid, frep, agent, event queue, RNG position,
+ * statistics) as one opaque blob of dca_checkpoint_size(h) bytes.  A blob can be loaded into any
+ * handle created with the same n_replicas, order and rng_mode; running on continues bit for bit. */
+size_t dca_checkpoint_size(const dca_handle *h);
+int dca_checkpoint_save(dca_handle *h, void *buf, size_t size);
+int dca_checkpoint_load(dca_handle *h, const void *buf, size_t size);
+
 /* ---- Gridfuncs / Gridneighs operators on explicit host arrays --------------- */
 /* Stateless device implementations of the reference's grid functions, for
  * callers and tests that work on arrays rather than a replica handle. */

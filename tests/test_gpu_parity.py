@@ -167,6 +167,28 @@ def test_reset_reproduces_the_run():
         assert np.array_equal(bits(w0), bits(sims.read_state(5)["w"]))
 
 
+def test_checkpoint_resume_continues_bit_for_bit():
+    from haskelldca_b200 import Opt, Replicas
+    from haskelldca_b200._ffi import DcaError
+
+    opt = dict(n_replicas=6, n_events=1200, order="fast", rng="philox", rng_seed=17, hoff_prob=0.1)
+    with Replicas(Opt(**opt)) as a:
+        a.run(500)
+        blob = a.checkpoint()
+        a.run(700)
+        want = [a.read_state(r) for r in range(6)]
+        summ = a.read_summary()
+    with Replicas(Opt(**opt)) as b:
+        b.restore(blob)
+        assert (b.read_summary()["iter"] == 500).all()
+        b.run(700)
+        for r in range(6):
+            assert_state_equal(b.read_state(r), want[r])
+        assert np.array_equal(b.read_summary()["stats"], summ["stats"])
+    with Replicas(Opt(**{**opt, "n_replicas": 5})) as c, pytest.raises(DcaError):
+        c.restore(blob)
+
+
 def test_stepwise_operators_follow_the_oracle_event_stream():
     """accFn1/accFn2 through dca_get_action / dca_grid_step_train with the host keeping the event generator
     (the reference's runStep shape, SimRunner.hs:60-97)."""
