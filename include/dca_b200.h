@@ -98,7 +98,7 @@ typedef struct {
   int32_t verify_reuse_constraint;
   int32_t verify_nelig_bounds;
   int32_t trace_capacity; /* per-replica trace records kept (0 = no tracing) */
-  int32_t warps_per_replica; /* 0 = library default */
+  int32_t warps_per_replica; /* accepted for compatibility and ignored: both kernels use 128-thread CTAs */
   double call_dur, call_dur_hoff, call_rate, hoff_prob; /* callDurNew, callDurHoff, callRate, hoffProb */
   float alpha_net, alpha_avg, alpha_grad;               /* alphaNet, alphaAvg, alphaGrad */
   const double *call_dur_v, *call_dur_hoff_v, *call_rate_v, *hoff_prob_v;
