@@ -425,6 +425,7 @@ struct EvRegs {
   float loss_sum, min_loss;
   double mean_new, call_dur, call_dur_hoff, hoff_prob;
   long long stats[8];                   // Stats counters (src/Stats.hs:15-30)
+  int dirty0, dirty1;                   // queue blocks whose minimum must be re-scanned (-1 = none)
   unsigned long long dbase;             // cached draws: lane l holds draw dbase + l ...
   unsigned long long dword;             // ... its random word (per lane)
   double dnl;                           // ... and -log(u) of that word (per lane)
@@ -597,9 +598,15 @@ __device__ __forceinline__ void q_build(SmemF& sm, unsigned n_end) {
   __syncwarp();
 }
 
-// random draws of the event are prepared while the agents evaluate its candidates
+// what the event warp does while the agents evaluate the candidates of `ev`: re-scan the queue
+// blocks the last pop touched (their minima are needed by the next push / pop) and make sure the
+// random draws of this event are cached
 __device__ __forceinline__ void ev_prepare(SmemF& sm, EvRegs& e, const Ev& ev) {
+  if (e.dirty0 >= 0) q_block_rescan(sm, (unsigned)e.dirty0);
+  if (e.dirty1 >= 0) q_block_rescan(sm, (unsigned)e.dirty1);
+  e.dirty0 = e.dirty1 = -1;
   if (ev.type != EV_END) ev_draws(e);
+  __syncwarp();
 }
 
 // environmentStep (Simulator.hs:101-134) for the event (type, cell, ev_ch,
@@ -700,8 +707,7 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx
       nx_type = EV_NEW; nx_cell = (int)slot;
       __syncwarp();
       if (lane == 0) { sm.q_time[slot] = CUDART_INF; sm.q_id[slot] = 0xFFFFFFFFu; }
-      __syncwarp();
-      q_block_rescan(sm, slot >> 5);
+      e.dirty0 = (int)(slot >> 5);
     } else {
       const int key = sm.q_key[slot];
       nx_type = EV_END; nx_cell = key >> 7; nx_ch = key & 127; nx_hoff = sm.q_hoff[slot];
@@ -721,9 +727,8 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx
         sm.q_id[last] = 0xFFFFFFFFu;
       }
       e.n_end--;
-      __syncwarp();
-      q_block_rescan(sm, slot >> 5);
-      if ((last >> 5) != (slot >> 5) && last_was_min) q_block_rescan(sm, last >> 5);
+      e.dirty0 = (int)(slot >> 5);
+      if ((last >> 5) != (slot >> 5) && last_was_min) e.dirty1 = (int)(last >> 5);
     }
   }
   if (lane == 0) {
@@ -875,6 +880,7 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
   e.mean_new = g->mean_new; e.call_dur = g->call_dur; e.call_dur_hoff = g->call_dur_hoff; e.hoff_prob = g->hoff_prob;
 #pragma unroll
   for (int k = 0; k < 8; ++k) e.stats[k] = g->stats[k];
+  e.dirty0 = e.dirty1 = -1;
   e.dbase = 0xFFFFFFFFFFFFFFF0ULL; e.dword = 0; e.dnl = 0.0;  // (empty draw cache)
   e.rng_mode = a.rng_mode; e.k0 = a.key0; e.k1 = a.key1; e.stream = g->stream;
   e.tape_w = nullptr; e.tape_l = nullptr; e.tape_len = 0;
