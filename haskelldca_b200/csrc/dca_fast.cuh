@@ -609,24 +609,32 @@ __device__ __forceinline__ void ev_prepare(SmemF& sm, EvRegs& e, const Ev& ev) {
   __syncwarp();
 }
 
-// environmentStep (Simulator.hs:101-134) for the event (type, cell, ev_ch,
-// ev_hoff, time) and the action `act` (-1 = Nothing); writes the next event to `nx`.
-__device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx, const int type, const int cell,
-                                                    const int ev_ch, const int ev_hoff, const double time,
-                                                    const int act) {
+// environmentStep (Simulator.hs:101-134) in three parts: the new events (ev_env_push), the pop of
+// the next event (ev_env_pop) -- neither depends on WHICH channel was chosen, only on whether the
+// call was accepted -- and the channel-dependent rest (ev_env_post: END key, reassign, grid bit).
+constexpr int CH_PENDING = 127;  // channel of the END event pushed by the current event: not chosen yet
+struct EnvNext {                 // the next event (registers, warp-uniform)
+  double time;
+  int type, cell, ch, hoff;
+  int pend_slot;                 // slot of the END event whose key still lacks the channel; -1 = none
+};
+
+// part 1: statistics and the new events (EventGen.hs:75-116)
+__device__ __forceinline__ int ev_env_push(SmemF& sm, EvRegs& e, const int type, const int cell, const double time,
+                                           const bool accepted) {
   const int lane = lane_id();
+  int pend_slot = -1;
   // Stats hooks, Stats.hs:61-81 as called from Simulator.hs:105-114
   if (type == EV_NEW) {
     e.stats[6]++; e.stats[0]++;
-    if (act >= 0) e.stats[1]++;
+    if (accepted) e.stats[1]++;
     else { e.stats[2]++; e.stats[7]++; }
   } else if (type == EV_HOFF) {
     e.stats[3]++;
-    if (act < 0) { e.stats[2]++; e.stats[7]++; }  // Simulator.hs:113
+    if (!accepted) { e.stats[2]++; e.stats[7]++; }  // Simulator.hs:113
   } else {
     e.stats[4]++;
   }
-  if (lane == 0 && act >= 0) sm.grid[cell][act >> 5] ^= 1u << (act & 31);  // executeAction, Gridfuncs.hs:105-110
   bool have_end = false;
   unsigned long long t_end = 0;
   unsigned id_end = 0;
@@ -638,7 +646,7 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx
     if (lane == 0) { sm.q_time[cell] = tn; sm.q_id[cell] = id_new; }
     q_block_push(sm, (unsigned)cell, (unsigned long long)__double_as_longlong(tn), id_new);
     unsigned used = 1;
-    if (act >= 0) {
+    if (accepted) {
       const unsigned long long w1 = ev_draw_word(e, 1);
       const double p = __dmul_rn((double)(w1 >> 11), 1.0 / 9007199254740992.0);  // Simulator.hs:121
       const double te = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 2), e.call_dur));  // callDurNew for both kinds, EventGen.hs:102,112
@@ -663,54 +671,54 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx
     }
     e.ndraws += used;
   } else if (type == EV_HOFF) {
-    if (act >= 0) {  // generateHoffEndEvent, EventGen.hs:114-116
+    if (accepted) {  // generateHoffEndEvent, EventGen.hs:114-116
       const double te = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 0), e.call_dur_hoff));
       t_end = (unsigned long long)__double_as_longlong(te);
       id_end = e.next_id++;
       have_end = true;
       e.ndraws += 1;
     }
-  } else if (act >= 0 && act != ev_ch) {
-    // END toCh, Simulator.hs:129-130: reassign cell act -> ev_ch (EventGen.hs:62-72): the call that
-    // used `act` continues on ev_ch, so its END event is re-keyed
-    if (lane == 0) {
-      const unsigned sl = sm.end_slot[cell][act];
-      sm.q_key[sl] = (uint16_t)((cell << 7) | ev_ch);
-      sm.end_slot[cell][ev_ch] = (uint16_t)sl;
-    }
   }
-  if (have_end) {  // push END (cell, act) [hoff] at slot QNEW + n_end
+  if (have_end) {  // push END (cell, <channel pending>) [hoff] at slot QNEW + n_end
     const unsigned slot = QNEW + e.n_end;
     if (slot < QCAP) {
       if (lane == 0) {
         sm.q_time[slot] = __longlong_as_double((long long)t_end);
         sm.q_id[slot] = id_end;
-        sm.q_key[slot] = (uint16_t)((cell << 7) | act);
+        sm.q_key[slot] = (uint16_t)((cell << 7) | CH_PENDING);
         sm.q_hoff[slot] = (uint8_t)end_hoff;
-        sm.end_slot[cell][act] = (uint16_t)slot;
       }
       q_block_push(sm, slot, t_end, id_end);
+      pend_slot = (int)slot;
     }
     e.n_end++;
   }
   __syncwarp();
-  // ---- the next event (Simulator.hs:132-134) ----
-  double nx_time;
-  int nx_type, nx_cell, nx_ch = -1, nx_hoff = HOFF_NONE;
+  return pend_slot;
+}
+
+// part 2: the next event (Simulator.hs:132-134)
+__device__ __forceinline__ EnvNext ev_env_pop(SmemF& sm, EvRegs& e, const int type, const int ev_hoff,
+                                              const double time, const int pend_slot) {
+  const int lane = lane_id();
+  EnvNext nx;
+  nx.pend_slot = pend_slot;
+  nx.ch = -1;
+  nx.hoff = HOFF_NONE;
   if (type == EV_END && ev_hoff != HOFF_NONE) {
     // the HOFF that follows a hand-off END: same time, next id (EventGen.hs:107-108)
-    nx_time = time; nx_type = EV_HOFF; nx_cell = ev_hoff;
+    nx.time = time; nx.type = EV_HOFF; nx.cell = ev_hoff;
   } else {  // pop, EventGen.hs:39-50
     const unsigned slot = q_min_slot(sm);
-    nx_time = sm.q_time[slot];
+    nx.time = sm.q_time[slot];
     if (slot < QNEW) {
-      nx_type = EV_NEW; nx_cell = (int)slot;
+      nx.type = EV_NEW; nx.cell = (int)slot;
       __syncwarp();
       if (lane == 0) { sm.q_time[slot] = CUDART_INF; sm.q_id[slot] = 0xFFFFFFFFu; }
       e.dirty0 = (int)(slot >> 5);
     } else {
       const int key = sm.q_key[slot];
-      nx_type = EV_END; nx_cell = key >> 7; nx_ch = key & 127; nx_hoff = sm.q_hoff[slot];
+      nx.type = EV_END; nx.cell = key >> 7; nx.ch = key & 127; nx.hoff = sm.q_hoff[slot];
       const unsigned last = QNEW + e.n_end - 1;
       const bool last_was_min = sm.bm_s[last >> 5] == last;
       __syncwarp();
@@ -721,18 +729,46 @@ __device__ __forceinline__ void ev_environment_step(SmemF& sm, EvRegs& e, Ev& nx
           sm.q_id[slot] = sm.q_id[last];
           sm.q_key[slot] = (uint16_t)lkey;
           sm.q_hoff[slot] = sm.q_hoff[last];
-          sm.end_slot[lkey >> 7][lkey & 127u] = (uint16_t)slot;
+          if ((lkey & 127u) != CH_PENDING) sm.end_slot[lkey >> 7][lkey & 127u] = (uint16_t)slot;
         }
         sm.q_time[last] = CUDART_INF;
         sm.q_id[last] = 0xFFFFFFFFu;
       }
+      if ((int)slot == nx.pend_slot) nx.pend_slot = -1;         // the END just pushed is the next event: not stored
+      else if ((int)last == nx.pend_slot) nx.pend_slot = (int)slot;  // ... or it moved into the hole
       e.n_end--;
       e.dirty0 = (int)(slot >> 5);
       if ((last >> 5) != (slot >> 5) && last_was_min) e.dirty1 = (int)(last >> 5);
     }
   }
+  __syncwarp();
+  return nx;
+}
+
+// the channel-dependent rest, once `act` (-1 = Nothing) is known; writes the next event to `out`
+__device__ __forceinline__ void ev_env_post(SmemF& sm, Ev& out, EnvNext nx, const int type, const int cell,
+                                            const int ev_ch, const int act) {
+  const int lane = lane_id();
+  if (nx.ch == CH_PENDING) nx.ch = act;  // the call accepted just now ends before anything else happens
+  bool rekey = false;
+  if (type == EV_END && act >= 0 && act != ev_ch) {
+    // END toCh, Simulator.hs:129-130: reassign cell act -> ev_ch (EventGen.hs:62-72): the call that used
+    // `act` continues on ev_ch, so its END event is re-keyed -- unless that event is the one just popped
+    if (nx.type == EV_END && nx.cell == cell && nx.ch == act) nx.ch = ev_ch;
+    else rekey = true;
+  }
   if (lane == 0) {
-    nx.time = nx_time; nx.type = nx_type; nx.cell = nx_cell; nx.ch = nx_ch; nx.hoff = nx_hoff;
+    if (act >= 0) sm.grid[cell][act >> 5] ^= 1u << (act & 31);  // executeAction, Gridfuncs.hs:105-110
+    if (nx.pend_slot >= 0) {
+      sm.q_key[nx.pend_slot] = (uint16_t)((cell << 7) | act);
+      sm.end_slot[cell][act] = (uint16_t)nx.pend_slot;
+    }
+    if (rekey) {
+      const unsigned sl = sm.end_slot[cell][act];
+      sm.q_key[sl] = (uint16_t)((cell << 7) | ev_ch);
+      sm.end_slot[cell][ev_ch] = (uint16_t)sl;
+    }
+    out.time = nx.time; out.type = nx.type; out.cell = nx.cell; out.ch = nx.ch; out.hoff = nx.hoff;
   }
   __syncwarp();
 }
@@ -925,6 +961,14 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
     dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
+#ifdef DCA_AGDELAY
+    {  // experiment: artificial dependent latency on the agents' update phase
+      int v = threadIdx.x;
+#pragma unroll 1
+      for (int i = 0; i < DCA_AGDELAY; ++i) v = __shfl_xor_sync(0xffffffffu, v, 1) + i;
+      if (v == 0x7fffffff) sm.status = -1;
+    }
+#endif
     if (sync_end) cta_barrier();
     cta_barrier();  // B1
     if (sm.status != ST_RUNNING) break;  // uniform
@@ -962,10 +1006,22 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const bool is_end = type == EV_END;
     const VTree vt = v_tree(sm);
     ev_prepare(sm, e, ev);
+    // (ev_env_push / ev_env_pop do not depend on the chosen channel and could run before B2; measured on
+    //  B200 that makes this warp the late one at B2: 245 / 233 M events/s instead of 251 M)
     cta_barrier();  // B2
     const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
-    ev_environment_step(sm, e, nx, type, cell, ev_ch, ev_hoff, time, d.act);  // Simulator.hs:101-134
+    const int pend_slot = ev_env_push(sm, e, type, cell, time, n > 0);       // Simulator.hs:101-128: new events
+    const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
+    ev_env_post(sm, nx, en, type, cell, ev_ch, d.act);                       // the channel-dependent rest
     ev_candidates(sm, nx, d.act);
+#ifdef DCA_EVDELAY
+    {  // experiment: artificial dependent latency on the event warp's update phase
+      int v = lane;
+#pragma unroll 1
+      for (int i = 0; i < DCA_EVDELAY; ++i) v = __shfl_xor_sync(0xffffffffu, v, 1) + i;
+      if (v == 0x7fffffff) sm.status = -1;
+    }
+#endif
     e.iter += 1;  // Simulator.hs:131
     // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
     int stop = ST_RUNNING;
