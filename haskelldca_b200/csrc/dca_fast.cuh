@@ -961,14 +961,6 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
     dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
-#ifdef DCA_AGDELAY
-    {  // experiment: artificial dependent latency on the agents' update phase
-      int v = threadIdx.x;
-#pragma unroll 1
-      for (int i = 0; i < DCA_AGDELAY; ++i) v = __shfl_xor_sync(0xffffffffu, v, 1) + i;
-      if (v == 0x7fffffff) sm.status = -1;
-    }
-#endif
     if (sync_end) cta_barrier();
     cta_barrier();  // B1
     if (sm.status != ST_RUNNING) break;  // uniform
@@ -1014,14 +1006,6 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
     ev_env_post(sm, nx, en, type, cell, ev_ch, d.act);                       // the channel-dependent rest
     ev_candidates(sm, nx, d.act);
-#ifdef DCA_EVDELAY
-    {  // experiment: artificial dependent latency on the event warp's update phase
-      int v = lane;
-#pragma unroll 1
-      for (int i = 0; i < DCA_EVDELAY; ++i) v = __shfl_xor_sync(0xffffffffu, v, 1) + i;
-      if (v == 0x7fffffff) sm.status = -1;
-    }
-#endif
     e.iter += 1;  // Simulator.hs:131
     // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
     int stop = ST_RUNNING;

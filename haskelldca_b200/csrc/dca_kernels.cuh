@@ -1,10 +1,14 @@
-// dca_kernels.cuh -- sm_100a kernels for the haskelldca per-event hot path.
+// dca_kernels.cuh -- sm_100a kernels shared by the whole library: the random source,
+// small helpers, mkSimState (k_init), featureRep, the Gridfuncs operators, read-back,
+// and the REFERENCE-ORDER run / step kernels (k_run<ORDER_REF>, k_step<ORDER_REF>):
+// the Accelerate Interpreter's arithmetic, operation for operation, used for the
+// --fixed_rng single-simulation replay.  The throughput kernel is in dca_fast.cuh.
 //
-// One CTA per replica; the replica's whole state (RepState) is staged in shared
-// memory for the duration of the launch and written back once.  Warp 0 runs the
-// event-sequential part of an event (candidate channels, afterstate values,
-// argmax, grid/frep update, event queue, RNG, stats); all warps run the dense
-// average-reward TDC update.  Reference: runStep, src/SimRunner.hs:60-97.
+// Reference-order kernels: one CTA per replica; the replica's whole state (RepState)
+// is staged in shared memory for the launch.  Warp 0 runs the event-sequential part
+// (candidate channels, argmax, grid/frep update, event queue, RNG, stats); one thread
+// per candidate folds its dense dot; all warps run the elementwise TDC update.
+// Reference: runStep, src/SimRunner.hs:60-97.
 //
 // All parity-critical fp32/fp64 arithmetic uses explicit round-to-nearest
 // intrinsics (never contracted); the file is also compiled with -fmad=false.
@@ -34,13 +38,8 @@ struct RunArgs {
   int trace_cap;
 };
 
-// Scratch that lives next to RepState in shared memory.
+// Scratch that lives next to RepState in shared memory (reference-order kernels).
 struct Scratch {
-  float R[512];    // row sums of x.w   (index f*7 + r)
-  float G[512];    // row sums of x.wg
-  float P[72];     // plane sums of x.w
-  float Pg[72];    // plane sums of x.wg
-  float Gs[16];    // group sums (w)
   float q[72];     // afterstate values of the candidates
   uint2 n4b[8];    // row byte masks: N4(cell) \ {cell}
   uint2 n2b[8];    // row byte masks: N2(cell) u {cell}
