@@ -322,3 +322,24 @@ def test_fast_and_ref_orders_agree_under_the_same_decisions():
     rel_avg = abs(float(got["avg_reward"]) - float(want["avg_reward"])) / abs(float(want["avg_reward"]))
     print(f"FAST vs REF under forced actions after {n} events: max |dw|/max|w| = {rel_w:.2e}, avg reward rel = {rel_avg:.2e}")
     assert rel_w < 1e-4 and rel_avg < 1e-4  # the tolerance BASELINE.json's north_star states
+
+
+@pytest.mark.parametrize("call_rate,call_dur,call_dur_hoff,hoff", [
+    (1000.0, 3.0, 1.0, 0.0),    # saturated: most arrivals are rejected, many events without a candidate
+    (40.0, 0.5, 0.2, 0.0),      # nearly empty grid: ~70 candidates on every arrival
+    (250.0, 6.0, 0.5, 0.5),     # half of the calls are handed off
+    (300.0, 10.0, 10.0, 0.9),   # long calls, almost always handed off: END+HOFF pairs dominate
+])
+def test_extreme_traffic_parameters_match_the_oracle(call_rate, call_dur, call_dur_hoff, hoff):
+    from haskelldca_b200 import Opt, Replicas
+
+    n_rep, n_ev = 3, 2500
+    kw = dict(call_rate=call_rate, call_dur=call_dur, call_dur_hoff=call_dur_hoff, hoff_prob=hoff)
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=77, trace=n_ev, **kw)) as sims:
+        sims.run(n_ev)
+        for r in range(n_rep):
+            o = po.Sim(po.default_opt(order=po.ORDER_FAST, rng_mode=po.RNG_PHILOX, seed=77, replica=r, n_events=n_ev, **kw))
+            status, done, tr = o.run(n_ev, trace=True)
+            assert done == n_ev and sims.read_status(r)[0] == status == po.SUCCESS
+            assert_trace_equal(sims.read_trace(r), tr)
+            assert_state_equal(sims.read_state(r), o.read())
