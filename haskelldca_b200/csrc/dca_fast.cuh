@@ -301,55 +301,108 @@ __device__ __forceinline__ VTree v_tree(const SmemF& sm) {
 // q[k] for every candidate: dense dot of afterstate k in the FAST tree, by
 // substituting the channel plane and the n_elig plane.  The 12 agent lane groups
 // take one candidate each per pass.
-__device__ __forceinline__ void q_eval(SmemF& sm, const Lane& l, const Ev& ev, const VTree& vt, const int n,
-                                       const bool is_end, const uint2 n4b_r, const uint2 n2b_r) {
-  const int grp = l.g8, r = l.r;
-  const int wfirst = l.vw * 4;  // first lane group of this warp
-  if (wfirst >= n) return;  // warp-uniform: this warp has no candidate at all
-  const bool rv = r < 7;
-  const int rc = rv ? r : 6;
+struct CandRows {  // one candidate's two re-evaluated planes, row r of this lane
+  float rowP, rowE;
+  int ch;
+  bool valid;
+};
+struct QConst {    // per-event constants of a lane in the candidate evaluation
+  uint2 x70;
+  float4 e_a, e_b;
+};
+__device__ __forceinline__ QConst q_const(const SmemF& sm, const int rc) {
+  QConst c;
+  c.x70 = *reinterpret_cast<const uint2*>(&sm.x[NCH * PLANE + rc * ROWPAD]);
+  c.e_a = *reinterpret_cast<const float4*>(&sm.w[0][(NCH * 7 + rc) * 4]);
+  c.e_b = *reinterpret_cast<const float4*>(&sm.w[1][(NCH * 7 + rc) * 4]);
+  return c;
+}
+__device__ __forceinline__ CandRows q_rows(const SmemF& sm, const Lane& l, const Ev& ev, const QConst& qc, const int k,
+                                           const int n, const bool is_end, const uint2 n4b_r, const uint2 n2b_r) {
+  const int rc = l.rv ? l.r : 6;
   const uint32_t want = is_end ? 1u : 0u;
-  const uint2 x70 = *reinterpret_cast<const uint2*>(&sm.x[NCH * PLANE + rc * ROWPAD]);
-  const float4 e_a = *reinterpret_cast<const float4*>(&sm.w[0][(NCH * 7 + rc) * 4]);
-  const float4 e_b = *reinterpret_cast<const float4*>(&sm.w[1][(NCH * 7 + rc) * 4]);
-#pragma unroll 1
-  for (int base = 0; base + wfirst < n; base += SLOTP) {  // warp-uniform trip count
-    const int k = base + grp;
-    const bool valid = k < n;
-    const int ch = ev.cand[valid ? k : n - 1];
-    const int row = ch * 7 + rc;
-    // channel plane: x' = x +- [cell in N4 \ {cell}]   (Gridfuncs.hs:212-217)
-    uint2 xr = *reinterpret_cast<const uint2*>(&sm.x[ch * PLANE + rc * ROWPAD]);
-    xr = is_end ? bsub(xr, n4b_r) : badd(xr, n4b_r);
-    const float4 wa = *reinterpret_cast<const float4*>(&sm.w[0][row * 4]);
-    const float4 wb = *reinterpret_cast<const float4*>(&sm.w[1][row * 4]);
-    const float rowP = rv ? rowdot2(cvt_row(xr), make_float2(wa.x, wa.y), make_float2(wa.z, wa.w),
-                                    make_float2(wb.x, wb.y), wb.z) : 0.0f;
-    // n_elig plane: e' = e -+ [cell in N2 u {cell} and ch eligible there on grid']  (Gridfuncs.hs:220-252)
-    const uint2 cr = *reinterpret_cast<const uint2*>(&sm.cnt2[ch * PLANE + rc * ROWPAD]);
-    const uint2 cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
-    const uint2 er = is_end ? badd(x70, cg) : bsub(x70, cg);
-    const float rowE = rv ? rowdot2(cvt_row(er), make_float2(e_a.x, e_a.y), make_float2(e_a.z, e_a.w),
-                                    make_float2(e_b.x, e_b.y), e_b.z) : 0.0f;
-    float Pp = rowP, Ep = rowE;
-#pragma unroll
-    for (int s = 1; s < 8; s <<= 1) {
-      Pp = __fadd_rn(Pp, __shfl_xor_sync(0xffffffffu, Pp, s));
-      Ep = __fadd_rn(Ep, __shfl_xor_sync(0xffffffffu, Ep, s));
-    }
-    // substitute leaf (ch & 31) of the V tree
-    const int lc = ch & 31, hi = ch >> 5;
-    const float p0 = hi == 0 ? Pp : sm.P[lc];
-    const float p1 = hi == 1 ? Pp : sm.P[lc + 32];
-    const float p2 = hi == 2 ? Pp : (lc < 6 ? sm.P[lc + 64] : 0.0f);
-    const float s0 = __shfl_sync(0xffffffffu, vt.sib[0], lc), s1 = __shfl_sync(0xffffffffu, vt.sib[1], lc),
-                s2 = __shfl_sync(0xffffffffu, vt.sib[2], lc), s3 = __shfl_sync(0xffffffffu, vt.sib[3], lc),
-                s4 = __shfl_sync(0xffffffffu, vt.sib[4], lc);
-    float b = __fadd_rn(__fadd_rn(p0, p1), p2);
-    b = __fadd_rn(b, s0); b = __fadd_rn(b, s1); b = __fadd_rn(b, s2); b = __fadd_rn(b, s3); b = __fadd_rn(b, s4);
-    const float qv = __fadd_rn(b, Ep);
-    if (r == 0 && valid) sm.q[k] = qv;
+  CandRows c;
+  c.valid = k < n;
+  c.ch = ev.cand[c.valid ? k : n - 1];
+  const int row = c.ch * 7 + rc;
+  // channel plane: x' = x +- [cell in N4 \ {cell}]   (Gridfuncs.hs:212-217)
+  uint2 xr = *reinterpret_cast<const uint2*>(&sm.x[c.ch * PLANE + rc * ROWPAD]);
+  xr = is_end ? bsub(xr, n4b_r) : badd(xr, n4b_r);
+  const float4 wa = *reinterpret_cast<const float4*>(&sm.w[0][row * 4]);
+  const float4 wb = *reinterpret_cast<const float4*>(&sm.w[1][row * 4]);
+  c.rowP = l.rv ? rowdot2(cvt_row(xr), make_float2(wa.x, wa.y), make_float2(wa.z, wa.w),
+                          make_float2(wb.x, wb.y), wb.z) : 0.0f;
+  // n_elig plane: e' = e -+ [cell in N2 u {cell} and ch eligible there on grid']  (Gridfuncs.hs:220-252)
+  const uint2 cr = *reinterpret_cast<const uint2*>(&sm.cnt2[c.ch * PLANE + rc * ROWPAD]);
+  const uint2 cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
+  const uint2 er = is_end ? badd(qc.x70, cg) : bsub(qc.x70, cg);
+  c.rowE = l.rv ? rowdot2(cvt_row(er), make_float2(qc.e_a.x, qc.e_a.y), make_float2(qc.e_a.z, qc.e_a.w),
+                          make_float2(qc.e_b.x, qc.e_b.y), qc.e_b.z) : 0.0f;
+  return c;
+}
+// substitute leaf (ch & 31) of the V tree by the re-evaluated channel plane, and plane 70 by Ep
+__device__ __forceinline__ float q_substitute(const SmemF& sm, const VTree& vt, const int ch, const float Pp,
+                                              const float Ep) {
+  const int lc = ch & 31, hi = ch >> 5;
+  const float p0 = hi == 0 ? Pp : sm.P[lc];
+  const float p1 = hi == 1 ? Pp : sm.P[lc + 32];
+  const float p2 = hi == 2 ? Pp : (lc < 6 ? sm.P[lc + 64] : 0.0f);
+  const float s0 = __shfl_sync(0xffffffffu, vt.sib[0], lc), s1 = __shfl_sync(0xffffffffu, vt.sib[1], lc),
+              s2 = __shfl_sync(0xffffffffu, vt.sib[2], lc), s3 = __shfl_sync(0xffffffffu, vt.sib[3], lc),
+              s4 = __shfl_sync(0xffffffffu, vt.sib[4], lc);
+  float b = __fadd_rn(__fadd_rn(p0, p1), p2);
+  b = __fadd_rn(b, s0); b = __fadd_rn(b, s1); b = __fadd_rn(b, s2); b = __fadd_rn(b, s3); b = __fadd_rn(b, s4);
+  return __fadd_rn(b, Ep);
+}
+// The agents' evaluation phase: V(s) and every q[k].  The V butterfly (5 steps) and the row
+// butterflies of the first pass of candidates (3 steps each) are independent shuffle chains and
+// are issued interleaved.
+__device__ __forceinline__ VTree q_phase(SmemF& sm, const Lane& l, const Ev& ev, const int n, const bool is_end,
+                                         const uint2 n4b_r, const uint2 n2b_r) {
+  const int lane = lane_id();
+  const int wfirst = l.vw * 4;    // first lane group of this warp
+  const bool have = wfirst < n;   // warp-uniform: this warp has a candidate in the first pass
+  VTree t;
+  const float p0 = sm.P[lane], p1 = sm.P[lane + 32];
+  const float p2 = lane < 6 ? sm.P[lane + 64] : 0.0f;
+  QConst qc;
+  CandRows c;
+  c.rowP = 0.0f; c.rowE = 0.0f; c.ch = 0; c.valid = false;
+  if (have) {
+    qc = q_const(sm, l.rv ? l.r : 6);
+    c = q_rows(sm, l, ev, qc, l.g8, n, is_end, n4b_r, n2b_r);
   }
+  float b = __fadd_rn(__fadd_rn(p0, p1), p2);
+  float Pp = c.rowP, Ep = c.rowE;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    t.sib[i] = __shfl_xor_sync(0xffffffffu, b, 1 << i);
+    b = __fadd_rn(b, t.sib[i]);
+    if (i < 3) {
+      Pp = __fadd_rn(Pp, __shfl_xor_sync(0xffffffffu, Pp, 1 << i));
+      Ep = __fadd_rn(Ep, __shfl_xor_sync(0xffffffffu, Ep, 1 << i));
+    }
+  }
+  t.val = __fadd_rn(b, sm.P[NCH]);
+  t.dotg = __fadd_rn(__fadd_rn(sm.Wg[0], sm.Wg[1]), sm.Wg[2]);
+  if (have) {
+    const float qv = q_substitute(sm, t, c.ch, Pp, Ep);
+    if (l.r == 0 && c.valid) sm.q[l.g8] = qv;
+#pragma unroll 1
+    for (int base = SLOTP; base + wfirst < n; base += SLOTP) {  // further passes (warp-uniform trip count)
+      const int k = base + l.g8;
+      c = q_rows(sm, l, ev, qc, k, n, is_end, n4b_r, n2b_r);
+      Pp = c.rowP; Ep = c.rowE;
+#pragma unroll
+      for (int s = 1; s < 8; s <<= 1) {
+        Pp = __fadd_rn(Pp, __shfl_xor_sync(0xffffffffu, Pp, s));
+        Ep = __fadd_rn(Ep, __shfl_xor_sync(0xffffffffu, Ep, s));
+      }
+      const float q2 = q_substitute(sm, t, c.ch, Pp, Ep);
+      if (l.r == 0 && c.valid) sm.q[k] = q2;
+    }
+  }
+  return t;
 }
 
 // argpmax (AccUtils.hs:203-208): the largest value, the LAST index among equals;
@@ -955,8 +1008,7 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const bool is_end = ev.type == EV_END;
     const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
     // accFn1 = getAction (Simulator.hs:154-172)
-    const VTree vt = v_tree(sm);
-    if (n > 0) q_eval(sm, l, ev, vt, n, is_end, n4b_r, n2b_r);
+    const VTree vt = q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r);
     cta_barrier();  // B2
     const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
@@ -1114,8 +1166,7 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   __syncthreads();
   const int n = ev.ncand;
   const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
-  const VTree vt = v_tree(sm);
-  if (n > 0 && wid != EVW) q_eval(sm, l, ev, vt, n, is_end, n4b_r, n2b_r);
+  const VTree vt = wid != EVW ? q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r) : v_tree(sm);
   __syncthreads();
   if (mode == 0) {
     float qb;
