@@ -260,19 +260,21 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
   }
   if (own_act) *reinterpret_cast<uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]) = is_end ? bsub(xb_act, n4b_r) : badd(xb_act, n4b_r);
   // plane sums: xor-butterfly 1,2,4 over the 8 lanes of a group, the six slots interleaved
+  // (the first three steps of the warp sum of x.wg ride along: independent shuffle chains)
 #pragma unroll
   for (int s = 1; s < 8; s <<= 1) {
 #pragma unroll
     for (int j = 0; j < NSLOT; ++j) rs[j] = __fadd_rn(rs[j], __shfl_xor_sync(0xffffffffu, rs[j], s));
+    rg_acc = __fadd_rn(rg_acc, __shfl_xor_sync(0xffffffffu, rg_acc, s));
   }
   if (l.r == 0) {
 #pragma unroll
     for (int j = 0; j < NSLOT; ++j)
       if (j < NSLOT - 1 || l.g8 != SLOTP - 1) sm.P[SLOTP * j + l.g8] = rs[j];
   }
-  // warp sum of x.wg: xor-butterfly 1,2,4,8,16
+  // warp sum of x.wg: xor-butterfly 1,2,4 (above), 8, 16
 #pragma unroll
-  for (int s = 1; s < 32; s <<= 1) rg_acc = __fadd_rn(rg_acc, __shfl_xor_sync(0xffffffffu, rg_acc, s));
+  for (int s = 8; s < 32; s <<= 1) rg_acc = __fadd_rn(rg_acc, __shfl_xor_sync(0xffffffffu, rg_acc, s));
   if (lane_id() == 0) sm.Wg[wid] = rg_acc;
 }
 
