@@ -51,5 +51,25 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str |
     return out
 
 
+HOST_DIR = os.path.join(os.path.dirname(HERE), "host")
+EXE = os.path.join(OUT_DIR, "dca-exe")
+
+
+def build_host(force: bool = False) -> str:
+    """g++ host/main.cpp (the C++ host layer + CLI over the C ABI) -> _build/dca-exe, linked against libdca_b200.so."""
+    srcs = [os.path.join(HOST_DIR, "main.cpp"), os.path.join(HOST_DIR, "dca_host.hpp"), LIB]
+    if not force and os.path.exists(EXE) and all(os.path.getmtime(EXE) >= os.path.getmtime(x) for x in srcs):
+        return EXE
+    gxx = shutil.which("g++") or "/usr/bin/g++"
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.check_call([gxx, "-std=c++17", "-O2", "-Wall", "-I", os.path.join(os.path.dirname(HERE), "include"),
+                           "-o", EXE, os.path.join(HOST_DIR, "main.cpp"), "-L", OUT_DIR, "-ldca_b200",
+                           "-Wl,-rpath,$ORIGIN"], env=env)
+    return EXE
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_host(force=True))
