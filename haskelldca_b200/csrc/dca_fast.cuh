@@ -503,29 +503,37 @@ __device__ __noinline__ unsigned long long ev_word_cold(int rng_mode, uint32_t k
 __device__ __forceinline__ unsigned long long ev_word(const EvRegs& e, unsigned long long d) {
   return ev_word_cold(e.rng_mode, e.k0, e.k1, e.stream, e.tape_w, e.tape_len, d);
 }
-// refill the draw cache: lane l <- draw dbase + l (cold: one refill serves ~19 events)
-__device__ __noinline__ void ev_refill(int rng_mode, uint32_t k0, uint32_t k1, unsigned long long stream,
+// refill the draw cache: lane l <- draw dbase + l (cold: one refill serves ~19 events).  Returns by
+// value: taking the address of EvRegs members would force the whole struct into local memory.
+struct Draw {
+  unsigned long long word;
+  double nl;
+};
+__device__ __noinline__ Draw ev_refill(int rng_mode, uint32_t k0, uint32_t k1, unsigned long long stream,
                                        const unsigned long long* tape_w, const double* tape_l,
-                                       unsigned long long tape_len, unsigned long long dbase,
-                                       unsigned long long* dword, double* dnl) {
+                                       unsigned long long tape_len, unsigned long long dbase) {
   const unsigned long long d = dbase + (unsigned long long)lane_id();
+  Draw r;
   if (rng_mode == RNG_PHILOX) {
-    *dword = philox_word(d, stream, k0, k1);
-    *dnl = neglog_u53(*dword);
+    r.word = philox_word(d, stream, k0, k1);
+    r.nl = neglog_u53(r.word);
   } else if (tape_len) {
     const unsigned long long i = d >= tape_len ? tape_len - 1 : d;
-    *dword = tape_w[i];
-    *dnl = tape_l[i];
+    r.word = tape_w[i];
+    r.nl = tape_l[i];
   } else {
-    *dword = 0ULL;
-    *dnl = 0.0;
+    r.word = 0ULL;
+    r.nl = 0.0;
   }
+  return r;
 }
 // make sure draws ndraws .. ndraws + 3 are cached
 __device__ __forceinline__ void ev_draws(EvRegs& e) {
   if (e.ndraws >= e.dbase && e.ndraws + 4 <= e.dbase + 32) return;  // warp-uniform
   e.dbase = e.ndraws;
-  ev_refill(e.rng_mode, e.k0, e.k1, e.stream, e.tape_w, e.tape_l, e.tape_len, e.dbase, &e.dword, &e.dnl);
+  const Draw r = ev_refill(e.rng_mode, e.k0, e.k1, e.stream, e.tape_w, e.tape_l, e.tape_len, e.dbase);
+  e.dword = r.word;
+  e.dnl = r.nl;
 }
 // draw ndraws + k: its word / its -log(u)   (k < 4 is always cached after ev_draws)
 __device__ __forceinline__ unsigned long long ev_draw_word(const EvRegs& e, unsigned k) {
