@@ -60,3 +60,36 @@ def test_config5_sweep_grid_of_replicas():
         o.run(n_ev)
         st = o.read()
         assert np.array_equal(st["stats"], whole["stats"][i]) and np.float32(st["avg_reward"]).view(np.uint32) == whole["avg_reward"][i].view(np.uint32)
+
+
+def test_allreduce_stats_over_two_devices_in_one_process():
+    """dca_allreduce_stats: one handle per device, ncclAllReduce of the int64[10] counters (the only collective
+    of the path).  Needs two GPUs; skipped on a one-GPU box."""
+    import ctypes as C
+
+    from haskelldca_b200 import _ffi
+
+    L = _ffi.load()
+    if L.dca_device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    n_rep, n_ev = 32, 1000
+    handles, totals = [], []
+    try:
+        for dev in range(2):
+            s = Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=4, device=dev,
+                             first_replica=dev * n_rep, hoff_prob=0.1))
+            s.run(n_ev)
+            handles.append(s)
+            totals.append(s.sum_stats()[0])
+        arr = (C.c_void_p * 2)(handles[0].h, handles[1].h)
+        out = np.zeros(10, dtype=np.int64)
+        _ffi.check(L.dca_allreduce_stats(arr, 2, _ffi.ptr(out)), handles[0].h)
+        assert np.array_equal(out, totals[0] + totals[1])
+        assert out[8] == 2 * n_rep * n_ev and out[9] == 0
+        # the same 64 replicas on one device give the same counters
+        with Replicas(Opt(n_replicas=2 * n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=4, hoff_prob=0.1)) as one:
+            one.run(n_ev)
+            assert np.array_equal(one.sum_stats()[0], out)
+    finally:
+        for s in handles:
+            s.close()
