@@ -35,12 +35,12 @@ def test_no_device_fails_loudly_instead_of_falling_back():
 
 
 def test_product_does_not_import_the_oracle():
-    pkg = os.path.join(ROOT, "haskelldca_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
-                src = open(os.path.join(dirpath, f)).read()
-                assert "pyoracle" not in src and "dca_oracle" not in src and "oracle/" not in src, f
+    for top in ("haskelldca_b200", "include", "host", "hs"):  # everything that ships
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".hs")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "pyoracle" not in src and "dca_oracle" not in src and "oracle/" not in src, f
 
 
 def test_neighbourhood_tables_host_side():
