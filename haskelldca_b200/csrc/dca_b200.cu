@@ -1026,3 +1026,14 @@ int dca_allreduce_stats(dca_handle** handles, int32_t n, int64_t out[10]) {
 }
 
 }  // extern "C"
+
+#ifdef DCA_PHASE_CLOCK
+extern "C" int dca_debug_phase(unsigned long long* out, int reset) {
+  if (cudaMemcpyFromSymbol(out, dca::fast::g_phase, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(dca::fast::g_phase, z, sizeof z);
+  }
+  return 0;
+}
+#endif

@@ -81,6 +81,23 @@ static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && o
 
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" ::: "memory"); }
 
+#ifdef DCA_PHASE_CLOCK  // development only: cycles per role (virtual warp) and phase, summed over CTAs and events
+__device__ unsigned long long g_phase[4][8];
+#define DCA_CLK(v) const long long v = clock64()
+// after a barrier: BAR.SYNC.DEFER_BLOCKING lets the warp run on to its first shared-memory access, so wait for one
+#define DCA_CLKB(v)                                            \
+  {                                                            \
+    const int s_ = *(volatile int*)&sm.status;                 \
+    if (s_ == 0x7ffffff0) asm volatile("trap;");               \
+  }                                                            \
+  const long long v = clock64()
+#define DCA_ACC(i, a, b) ph[i] += (unsigned long long)((b) - (a))
+#else
+#define DCA_CLK(v)
+#define DCA_CLKB(v)
+#define DCA_ACC(i, a, b)
+#endif
+
 // ---------------------------------------------------------------------------
 // packed fp32 helpers
 // ---------------------------------------------------------------------------
@@ -182,7 +199,8 @@ __device__ __forceinline__ Lane make_lane() {
 // Without UPDATE only the sums of the current state are formed.
 template <bool UPDATE>
 __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, const int act, const bool is_end,
-                                           const TdScalars td, const uint2 n4b_r, const uint2 n2b_r) {
+                                           const TdScalars td, const uint2 n4b_r, const uint2 n2b_r,
+                                           long long* clk_mid = nullptr) {
   const int wid = l.vw;
   // the warp-slot that holds plane `act` (warp-uniform)
   int ja = -1, wact = -1;
@@ -194,6 +212,9 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
   float rg_acc = 0.0f;
   // does this lane own a row of plane `act`?  (plane f lives on group f % 12 for f < 60, f - 60 above)
   const bool own_act = UPDATE && act >= 0 && l.rv && l.g8 == (act >= SLOTP * (NSLOT - 1) ? act - SLOTP * (NSLOT - 1) : act % SLOTP);
+  const Row7 dm = cvt_row(n4b_r);            // the row of N4 \ {cell} as 0.0 / 1.0
+  const float sgn = is_end ? -1.0f : 1.0f;
+  (void)ja; (void)wact; (void)dm; (void)sgn;
   uint2 xb_act = make_uint2(0, 0);
   if (own_act) xb_act = *reinterpret_cast<const uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]);
 #pragma unroll
@@ -213,11 +234,21 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     const Row7 xo = cvt_row(xb);
     Row7 xn = xo;
     if (UPDATE) {
+#ifdef DCA_ACT_BRANCH
       if (j == ja && wid == wact) {  // warp-uniform: this warp's slot j holds plane `act`
         if (f == act) xn = cvt_row(is_end ? bsub(xb, n4b_r) : badd(xb, n4b_r));
       }
+#else
+      // x' = x + s * [cell in N4 \ {cell}], s = +-1 on plane `act` and 0 elsewhere: small integers, exact in
+      // fp32, and branch-free, so that the six slot bodies form one basic block
+      const float sa = f == act ? sgn : 0.0f;
+      xn.a = __ffma2_rn(f2(sa), dm.a, xo.a);
+      xn.b = __ffma2_rn(f2(sa), dm.b, xo.b);
+      xn.c = __ffma2_rn(f2(sa), dm.c, xo.c);
+      xn.d = __fmaf_rn(sa, dm.d, xo.d);
+#endif
       if (last && wid == 2 && act >= 0) {  // warp-uniform: the owners of plane 70 (n_elig) and of cnt2[act]
-        if (f == NCH && pv) {
+        if (f == NCH) {  // (the shadow lanes -- row 7, group 11 -- compute and store the same values as their originals)
           const int co = act * PLANE + (l.rv ? l.r : 6) * ROWPAD;
           const uint2 cr = *reinterpret_cast<const uint2*>(&sm.cnt2[co]);
           const uint32_t want = is_end ? 1u : 0u;
@@ -225,10 +256,8 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
           const uint2 cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
           const uint2 eb = is_end ? badd(xb, cg) : bsub(xb, cg);
           xn = cvt_row(eb);
-          if (l.rv) {
-            *reinterpret_cast<uint2*>(&sm.x[xo_]) = eb;
-            *reinterpret_cast<uint2*>(&sm.cnt2[co]) = is_end ? bsub(cr, n2b_r) : badd(cr, n2b_r);
-          }
+          *reinterpret_cast<uint2*>(&sm.x[xo_]) = eb;
+          *reinterpret_cast<uint2*>(&sm.cnt2[co]) = is_end ? bsub(cr, n2b_r) : badd(cr, n2b_r);
         }
       }
 #define DCA_UPD2(W, G, XN, XO)                                            \
@@ -248,10 +277,10 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
         w6 = __fsub_rn(w6, g_);
         ag.g6[j] = __fmaf_rn(td.sg, xo.d, ag.g6[j]);
       }
-      if (valid) {
-        *reinterpret_cast<float4*>(&sm.w[0][wo_]) = make_float4(w01.x, w01.y, w23.x, w23.y);
-        *reinterpret_cast<float4*>(&sm.w[1][wo_]) = make_float4(w45.x, w45.y, w6, 0.0f);
-      }
+      // unconditional: a shadow lane (row 7 -> row 6, group 11 in the last slot -> plane 70) holds the same
+      // x, w and wGradCorr as its original and stores the same values to the same address
+      *reinterpret_cast<float4*>(&sm.w[0][wo_]) = make_float4(w01.x, w01.y, w23.x, w23.y);
+      *reinterpret_cast<float4*>(&sm.w[1][wo_]) = make_float4(w45.x, w45.y, w6, 0.0f);
     }
     rs[j] = valid ? rowdot2(xn, w01, w23, w45, w6) : 0.0f;
     const float rg = rowdot2(xn, ag.g01[j], ag.g23[j], ag.g45[j], ag.g6[j]);
@@ -259,6 +288,15 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     else if (valid) rg_acc = __fadd_rn(rg_acc, rg);
   }
   if (own_act) *reinterpret_cast<uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]) = is_end ? bsub(xb_act, n4b_r) : badd(xb_act, n4b_r);
+#ifdef DCA_PHASE_CLOCK
+  if (clk_mid) {  // wait for the row sums, then stamp
+    float s_ = rg_acc;
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) s_ += rs[j];
+    if (s_ == 1.2345e-30f) asm volatile("trap;");
+    *clk_mid = clock64();
+  }
+#endif
   // plane sums: xor-butterfly 1,2,4 over the 8 lanes of a group, the six slots interleaved
   // (the first three steps of the warp sum of x.wg ride along: independent shuffle chains)
 #pragma unroll
@@ -303,11 +341,6 @@ __device__ __forceinline__ VTree v_tree(const SmemF& sm) {
 // q[k] for every candidate: dense dot of afterstate k in the FAST tree, by
 // substituting the channel plane and the n_elig plane.  The 12 agent lane groups
 // take one candidate each per pass.
-struct CandRows {  // one candidate's two re-evaluated planes, row r of this lane
-  float rowP, rowE;
-  int ch;
-  bool valid;
-};
 struct QConst {    // per-event constants of a lane in the candidate evaluation
   uint2 x70;
   float4 e_a, e_b;
@@ -319,36 +352,50 @@ __device__ __forceinline__ QConst q_const(const SmemF& sm, const int rc) {
   c.e_b = *reinterpret_cast<const float4*>(&sm.w[1][(NCH * 7 + rc) * 4]);
   return c;
 }
-__device__ __forceinline__ CandRows q_rows(const SmemF& sm, const Lane& l, const Ev& ev, const QConst& qc, const int k,
-                                           const int n, const bool is_end, const uint2 n4b_r, const uint2 n2b_r) {
-  const int rc = l.rv ? l.r : 6;
-  const uint32_t want = is_end ? 1u : 0u;
-  CandRows c;
-  c.valid = k < n;
-  c.ch = ev.cand[c.valid ? k : n - 1];
-  const int row = c.ch * 7 + rc;
-  // channel plane: x' = x +- [cell in N4 \ {cell}]   (Gridfuncs.hs:212-217)
-  uint2 xr = *reinterpret_cast<const uint2*>(&sm.x[c.ch * PLANE + rc * ROWPAD]);
-  xr = is_end ? bsub(xr, n4b_r) : badd(xr, n4b_r);
-  const float4 wa = *reinterpret_cast<const float4*>(&sm.w[0][row * 4]);
-  const float4 wb = *reinterpret_cast<const float4*>(&sm.w[1][row * 4]);
-  c.rowP = l.rv ? rowdot2(cvt_row(xr), make_float2(wa.x, wa.y), make_float2(wa.z, wa.w),
-                          make_float2(wb.x, wb.y), wb.z) : 0.0f;
-  // n_elig plane: e' = e -+ [cell in N2 u {cell} and ch eligible there on grid']  (Gridfuncs.hs:220-252)
-  const uint2 cr = *reinterpret_cast<const uint2*>(&sm.cnt2[c.ch * PLANE + rc * ROWPAD]);
-  const uint2 cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
-  const uint2 er = is_end ? badd(qc.x70, cg) : bsub(qc.x70, cg);
-  c.rowE = l.rv ? rowdot2(cvt_row(er), make_float2(qc.e_a.x, qc.e_a.y), make_float2(qc.e_a.z, qc.e_a.w),
-                          make_float2(qc.e_b.x, qc.e_b.y), qc.e_b.z) : 0.0f;
+// Everything one candidate channel needs from shared memory, loaded up front (one round trip after the
+// channel number is known): row rc of its feature plane, of its weights and of cnt2, and the three plane
+// sums that share its leaf of the V tree.
+struct CandLoads {
+  uint2 xr, cr;
+  float4 wa, wb;
+  float l0, l1, l2;
+};
+__device__ __forceinline__ CandLoads q_loads(const SmemF& sm, const int ch, const int rc) {
+  CandLoads c;
+  const int row = ch * 7 + rc, lc = ch & 31;
+  c.xr = *reinterpret_cast<const uint2*>(&sm.x[ch * PLANE + rc * ROWPAD]);
+  c.cr = *reinterpret_cast<const uint2*>(&sm.cnt2[ch * PLANE + rc * ROWPAD]);
+  c.wa = *reinterpret_cast<const float4*>(&sm.w[0][row * 4]);
+  c.wb = *reinterpret_cast<const float4*>(&sm.w[1][row * 4]);
+  c.l0 = sm.P[lc];
+  c.l1 = sm.P[lc + 32];
+  c.l2 = sm.P[lc < 6 ? lc + 64 : NCH + 1];  // P[71] == 0
   return c;
 }
+// row rc of the two re-evaluated planes of afterstate `ch` (branch-free; a row-7 lane shadows row 6 and is
+// masked at the end)
+__device__ __forceinline__ void q_rows(const CandLoads& c, const QConst& qc, const bool rv, const bool is_end,
+                                       const uint2 n4b_r, const uint2 n2b_r, float& rowP, float& rowE) {
+  const uint32_t want = is_end ? 1u : 0u;
+  // channel plane: x' = x +- [cell in N4 \ {cell}]   (Gridfuncs.hs:212-217)
+  const uint2 xr = is_end ? bsub(c.xr, n4b_r) : badd(c.xr, n4b_r);
+  const float rp = rowdot2(cvt_row(xr), make_float2(c.wa.x, c.wa.y), make_float2(c.wa.z, c.wa.w),
+                           make_float2(c.wb.x, c.wb.y), c.wb.z);
+  // n_elig plane: e' = e -+ [cell in N2 u {cell} and ch eligible there on grid']  (Gridfuncs.hs:220-252)
+  const uint2 cg = make_uint2(n2b_r.x & eq_bytes(c.cr.x, want), n2b_r.y & eq_bytes(c.cr.y, want));
+  const uint2 er = is_end ? badd(qc.x70, cg) : bsub(qc.x70, cg);
+  const float re = rowdot2(cvt_row(er), make_float2(qc.e_a.x, qc.e_a.y), make_float2(qc.e_a.z, qc.e_a.w),
+                           make_float2(qc.e_b.x, qc.e_b.y), qc.e_b.z);
+  rowP = rv ? rp : 0.0f;
+  rowE = rv ? re : 0.0f;
+}
 // substitute leaf (ch & 31) of the V tree by the re-evaluated channel plane, and plane 70 by Ep
-__device__ __forceinline__ float q_substitute(const SmemF& sm, const VTree& vt, const int ch, const float Pp,
+__device__ __forceinline__ float q_substitute(const CandLoads& c, const VTree& vt, const int ch, const float Pp,
                                               const float Ep) {
   const int lc = ch & 31, hi = ch >> 5;
-  const float p0 = hi == 0 ? Pp : sm.P[lc];
-  const float p1 = hi == 1 ? Pp : sm.P[lc + 32];
-  const float p2 = hi == 2 ? Pp : (lc < 6 ? sm.P[lc + 64] : 0.0f);
+  const float p0 = hi == 0 ? Pp : c.l0;
+  const float p1 = hi == 1 ? Pp : c.l1;
+  const float p2 = hi == 2 ? Pp : c.l2;
   const float s0 = __shfl_sync(0xffffffffu, vt.sib[0], lc), s1 = __shfl_sync(0xffffffffu, vt.sib[1], lc),
               s2 = __shfl_sync(0xffffffffu, vt.sib[2], lc), s3 = __shfl_sync(0xffffffffu, vt.sib[3], lc),
               s4 = __shfl_sync(0xffffffffu, vt.sib[4], lc);
@@ -358,24 +405,29 @@ __device__ __forceinline__ float q_substitute(const SmemF& sm, const VTree& vt, 
 }
 // The agents' evaluation phase: V(s) and every q[k].  The V butterfly (5 steps) and the row
 // butterflies of the first pass of candidates (3 steps each) are independent shuffle chains and
-// are issued interleaved.
+// are issued interleaved.  Candidate k of a pass sits on lane group k % 12; its channel number is
+// read before the candidate count is known (a stale entry is a valid channel and is masked later).
 __device__ __forceinline__ VTree q_phase(SmemF& sm, const Lane& l, const Ev& ev, const int n, const bool is_end,
                                          const uint2 n4b_r, const uint2 n2b_r) {
   const int lane = lane_id();
+  const int rc = l.rv ? l.r : 6;
   const int wfirst = l.vw * 4;    // first lane group of this warp
   const bool have = wfirst < n;   // warp-uniform: this warp has a candidate in the first pass
   VTree t;
+  int ch = ev.cand[l.g8];
   const float p0 = sm.P[lane], p1 = sm.P[lane + 32];
   const float p2 = lane < 6 ? sm.P[lane + 64] : 0.0f;
+  const float p70 = sm.P[NCH];
+  const float wg0 = sm.Wg[0], wg1 = sm.Wg[1], wg2 = sm.Wg[2];
   QConst qc;
-  CandRows c;
-  c.rowP = 0.0f; c.rowE = 0.0f; c.ch = 0; c.valid = false;
+  CandLoads c;
+  float Pp = 0.0f, Ep = 0.0f;
   if (have) {
-    qc = q_const(sm, l.rv ? l.r : 6);
-    c = q_rows(sm, l, ev, qc, l.g8, n, is_end, n4b_r, n2b_r);
+    qc = q_const(sm, rc);
+    c = q_loads(sm, ch, rc);
+    q_rows(c, qc, l.rv, is_end, n4b_r, n2b_r, Pp, Ep);
   }
   float b = __fadd_rn(__fadd_rn(p0, p1), p2);
-  float Pp = c.rowP, Ep = c.rowE;
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
     t.sib[i] = __shfl_xor_sync(0xffffffffu, b, 1 << i);
@@ -385,23 +437,24 @@ __device__ __forceinline__ VTree q_phase(SmemF& sm, const Lane& l, const Ev& ev,
       Ep = __fadd_rn(Ep, __shfl_xor_sync(0xffffffffu, Ep, 1 << i));
     }
   }
-  t.val = __fadd_rn(b, sm.P[NCH]);
-  t.dotg = __fadd_rn(__fadd_rn(sm.Wg[0], sm.Wg[1]), sm.Wg[2]);
+  t.val = __fadd_rn(b, p70);
+  t.dotg = __fadd_rn(__fadd_rn(wg0, wg1), wg2);
   if (have) {
-    const float qv = q_substitute(sm, t, c.ch, Pp, Ep);
-    if (l.r == 0 && c.valid) sm.q[l.g8] = qv;
+    const float qv = q_substitute(c, t, ch, Pp, Ep);
+    if (l.r == 0 && l.g8 < n) sm.q[l.g8] = qv;
 #pragma unroll 1
     for (int base = SLOTP; base + wfirst < n; base += SLOTP) {  // further passes (warp-uniform trip count)
       const int k = base + l.g8;
-      c = q_rows(sm, l, ev, qc, k, n, is_end, n4b_r, n2b_r);
-      Pp = c.rowP; Ep = c.rowE;
+      ch = ev.cand[k];
+      c = q_loads(sm, ch, rc);
+      q_rows(c, qc, l.rv, is_end, n4b_r, n2b_r, Pp, Ep);
 #pragma unroll
       for (int s = 1; s < 8; s <<= 1) {
         Pp = __fadd_rn(Pp, __shfl_xor_sync(0xffffffffu, Pp, s));
         Ep = __fadd_rn(Ep, __shfl_xor_sync(0xffffffffu, Ep, s));
       }
-      const float q2 = q_substitute(sm, t, c.ch, Pp, Ep);
-      if (l.r == 0 && c.valid) sm.q[k] = q2;
+      const float q2 = q_substitute(c, t, ch, Pp, Ep);
+      if (l.r == 0 && k < n) sm.q[k] = q2;
     }
   }
   return t;
@@ -920,7 +973,9 @@ __device__ __forceinline__ void stage_in(SmemF& sm, const RepState* g) {
   copy16(sm.q_id, g->q_id, sizeof g->q_id);
   copy16(sm.q_key, g->q_key, sizeof sm.q_key);
   copy8(sm.q_hoff, g->q_hoff, sizeof sm.q_hoff);
+  if (threadIdx.x < 72) sm.ev[0].cand[threadIdx.x] = sm.ev[1].cand[threadIdx.x] = 0;  // (read before ncand is known)
   if (threadIdx.x == 0) {
+    sm.P[NCH + 1] = 0.0f;  // the pad leaf of the V tree
     Ev& ev = sm.ev[0];
     ev.time = g->ev_time; ev.type = g->ev_type; ev.cell = g->ev_cell; ev.ch = g->ev_ch; ev.hoff = g->ev_hoff;
     ev.ncand = 0;
@@ -1012,21 +1067,41 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
   dense_pass<false>(sm, ag, l, -1, false, TdScalars{0.f, 0.f, 0.f, 0.f}, make_uint2(0, 0), make_uint2(0, 0));
   cta_barrier();  // B1
 #pragma unroll 1
+#ifdef DCA_PHASE_CLOCK
+  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   for (long long it = 0; it < a.max_events; ++it) {
+    DCA_CLK(c0);
     const Ev& ev = sm.ev[it & 1];
     const int n = ev.ncand;
     const bool is_end = ev.type == EV_END;
     const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
     // accFn1 = getAction (Simulator.hs:154-172)
     const VTree vt = q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r);
+    DCA_CLK(c1);
     cta_barrier();  // B2
+    DCA_CLKB(c2);
     const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
+    DCA_CLK(c3);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
+#ifdef DCA_PHASE_CLOCK
+    long long cm;
+    dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r, &cm);
+    ph[6] += (unsigned long long)(cm - c3);
+#else
     dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
+#endif
+    DCA_CLK(c4);
     if (sync_end) cta_barrier();
     cta_barrier();  // B1
+    DCA_CLKB(c5);
+    DCA_ACC(0, c0, c1); DCA_ACC(1, c1, c2); DCA_ACC(2, c2, c3); DCA_ACC(3, c3, c4); DCA_ACC(4, c4, c5); DCA_ACC(5, c0, c5);
     if (sm.status != ST_RUNNING) break;  // uniform
   }
+#ifdef DCA_PHASE_CLOCK
+  if (lane_id() == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_phase[l.vw][i], ph[i]);
+#endif
   cta_barrier();
   stage_out(sm, g);
   store_wg(ag, g, l);
@@ -1050,6 +1125,9 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   ev_candidates(sm, sm.ev[0], -1);
   cta_barrier();  // B1
   long long it = 0;
+#ifdef DCA_PHASE_CLOCK
+  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 #pragma unroll 1
   for (; it < a.max_events; ++it) {
     const Ev& ev = sm.ev[it & 1];
@@ -1058,12 +1136,16 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const int ev_ch = ev.ch, ev_hoff = ev.hoff;
     const double time = ev.time;
     const bool is_end = type == EV_END;
+    DCA_CLK(c0);
     const VTree vt = v_tree(sm);
     ev_prepare(sm, e, ev);
+    DCA_CLK(c1);
     // (ev_env_push / ev_env_pop do not depend on the chosen channel and could run before B2; measured on
     //  B200 that makes this warp the late one at B2: 245 / 233 M events/s instead of 251 M)
     cta_barrier();  // B2
+    DCA_CLKB(c2);
     const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
+    DCA_CLK(c3);
     const int pend_slot = ev_env_push(sm, e, type, cell, time, n > 0);       // Simulator.hs:101-128: new events
     const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
     ev_env_post(sm, nx, en, type, cell, ev_ch, d.act);                       // the channel-dependent rest
@@ -1106,9 +1188,16 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     if (stop == ST_RUNNING && e.iter == e.n_events) stop = ST_SUCCESS;
     if (stop == ST_RUNNING && e.rng_mode == RNG_TAPE && e.ndraws + 8 > e.tape_len) stop = ST_TAPE_EXHAUSTED;
     if (lane == 0) sm.status = stop;
+    DCA_CLK(c4);
     cta_barrier();  // B1
+    DCA_CLKB(c5);
+    DCA_ACC(0, c0, c1); DCA_ACC(1, c1, c2); DCA_ACC(2, c2, c3); DCA_ACC(3, c3, c4); DCA_ACC(4, c4, c5); DCA_ACC(5, c0, c5);
     if (stop != ST_RUNNING) { ++it; break; }
   }
+#ifdef DCA_PHASE_CLOCK
+  if (lane == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_phase[3][i], ph[i]);
+#endif
   cta_barrier();
   stage_out(sm, g);
   if (lane == 0) {
