@@ -202,21 +202,12 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
                                            const TdScalars td, const uint2 n4b_r, const uint2 n2b_r,
                                            long long* clk_mid = nullptr) {
   const int wid = l.vw;
-  // the warp-slot that holds plane `act` (warp-uniform)
-  int ja = -1, wact = -1;
-  if (UPDATE && act >= 0) {
-    ja = act >= SLOTP * (NSLOT - 1) ? NSLOT - 1 : act / SLOTP;
-    wact = (act - SLOTP * ja) >> 2;
-  }
   float rs[NSLOT];
   float rg_acc = 0.0f;
-  // does this lane own a row of plane `act`?  (plane f lives on group f % 12 for f < 60, f - 60 above)
-  const bool own_act = UPDATE && act >= 0 && l.rv && l.g8 == (act >= SLOTP * (NSLOT - 1) ? act - SLOTP * (NSLOT - 1) : act % SLOTP);
   const Row7 dm = cvt_row(n4b_r);            // the row of N4 \ {cell} as 0.0 / 1.0
   const float sgn = is_end ? -1.0f : 1.0f;
-  (void)ja; (void)wact; (void)dm; (void)sgn;
-  uint2 xb_act = make_uint2(0, 0);
-  if (own_act) xb_act = *reinterpret_cast<const uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]);
+  bool own_act = false;                      // does this lane own a row of plane `act`?
+  (void)dm; (void)sgn;
 #pragma unroll
   for (int j = 0; j < NSLOT; ++j) {
     const bool last = j == NSLOT - 1;
@@ -234,19 +225,14 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     const Row7 xo = cvt_row(xb);
     Row7 xn = xo;
     if (UPDATE) {
-#ifdef DCA_ACT_BRANCH
-      if (j == ja && wid == wact) {  // warp-uniform: this warp's slot j holds plane `act`
-        if (f == act) xn = cvt_row(is_end ? bsub(xb, n4b_r) : badd(xb, n4b_r));
-      }
-#else
       // x' = x + s * [cell in N4 \ {cell}], s = +-1 on plane `act` and 0 elsewhere: small integers, exact in
       // fp32, and branch-free, so that the six slot bodies form one basic block
       const float sa = f == act ? sgn : 0.0f;
+      own_act = own_act || f == act;
       xn.a = __ffma2_rn(f2(sa), dm.a, xo.a);
       xn.b = __ffma2_rn(f2(sa), dm.b, xo.b);
       xn.c = __ffma2_rn(f2(sa), dm.c, xo.c);
       xn.d = __fmaf_rn(sa, dm.d, xo.d);
-#endif
       if (last && wid == 2 && act >= 0) {  // warp-uniform: the owners of plane 70 (n_elig) and of cnt2[act]
         if (f == NCH) {  // (the shadow lanes -- row 7, group 11 -- compute and store the same values as their originals)
           const int co = act * PLANE + (l.rv ? l.r : 6) * ROWPAD;
@@ -287,7 +273,11 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     if (j == 0) rg_acc = l.rv ? rg : 0.0f;
     else if (valid) rg_acc = __fadd_rn(rg_acc, rg);
   }
-  if (own_act) *reinterpret_cast<uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]) = is_end ? bsub(xb_act, n4b_r) : badd(xb_act, n4b_r);
+  if (UPDATE && own_act && l.rv) {  // the afterstate row of plane `act` (every slot has read its x by now)
+    uint2* xp = reinterpret_cast<uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]);
+    const uint2 xb_act = *xp;
+    *xp = is_end ? bsub(xb_act, n4b_r) : badd(xb_act, n4b_r);
+  }
 #ifdef DCA_PHASE_CLOCK
   if (clk_mid) {  // wait for the row sums, then stamp
     float s_ = rg_acc;
@@ -462,7 +452,10 @@ __device__ __forceinline__ VTree q_phase(SmemF& sm, const Lane& l, const Ev& ev,
 
 // argpmax (AccUtils.hs:203-208): the largest value, the LAST index among equals;
 // NaNs follow the sequential right fold exactly.  Every warp computes it for itself.
-__device__ __forceinline__ int argmax_last_warp(const float* q, int n, float& qbest) {
+// cand_lane = cand[lane] (read before the barrier): the chosen channel rides along in the index
+// reduction, and the best value is rebuilt from the reduced key, so that nothing is loaded or
+// shuffled after the two reductions.  Returns the channel; qbest = q[k].
+__device__ __forceinline__ int argmax_last_warp(const float* q, const uint8_t* cand, int cand_lane, int n, float& qbest) {
   const int lane = lane_id();
   float bq = -CUDART_INF_F;
   int bk = -1;
@@ -472,7 +465,7 @@ __device__ __forceinline__ int argmax_last_warp(const float* q, int n, float& qb
 #pragma unroll 1
     for (int k = lane; k < n; k += 32) {
       const float v = q[k];
-      if (v >= bq || v != v) { bq = v; bk = k; }  // (a NaN is kept so that the slow path is taken)
+      if (v >= bq || v != v) { bq = v; bk = k; cand_lane = cand[k]; }  // (a NaN is kept so that the slow path is taken)
     }
   }
   if (__any_sync(0xffffffffu, bq != bq)) {
@@ -481,7 +474,7 @@ __device__ __forceinline__ int argmax_last_warp(const float* q, int n, float& qb
     for (int i = n - 2; i >= 0; --i)
       if (q[i] > q[best]) best = i;
     qbest = q[best];
-    return best;
+    return cand[best];
   }
   // order-preserving map float -> uint32, then two warp reductions
   uint32_t u = __float_as_uint(bq);
@@ -489,9 +482,11 @@ __device__ __forceinline__ int argmax_last_warp(const float* q, int n, float& qb
   if (bq == 0.0f) u = 0x80000000u;  // -0 == +0
   if (bk < 0) u = 0u;
   const uint32_t m = __reduce_max_sync(0xffffffffu, u);
-  const int k = __reduce_max_sync(0xffffffffu, (u == m) ? bk : -1);
-  qbest = __shfl_sync(0xffffffffu, bq, k & 31);
-  return k;
+  const int key = __reduce_max_sync(0xffffffffu, (u == m) ? ((bk << 8) | cand_lane) : -1);
+  // the inverse map gives q[k] bit for bit, except that a best value of -0 comes back as +0: it is only
+  // ever added to reward - avgR, which is never -0, so the sum is the same
+  qbest = __uint_as_float((m & 0x80000000u) ? (m & 0x7FFFFFFFu) : ~m);
+  return key & 0xFF;
 }
 
 // what every thread derives from the Q phase: the action and the TD scalars
@@ -501,14 +496,13 @@ struct Decision {
   TdScalars td;
 };
 __device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const VTree& vt, int n, bool is_end,
-                                           float& avgR, int& ncalls) {
+                                           float& avgR, int& ncalls, const int cand_lane) {
   const float alpha_net = sm.alpha_net, alpha_avg = sm.alpha_avg, alpha_grad = sm.alpha_grad;
   Decision d;
   d.act = -1;
   float next_val = vt.val;  // no action: nextFrep = frep (Simulator.hs:170-171)
   if (n > 0) {
-    const int k = argmax_last_warp(sm.q, n, next_val);  // selectAction, Simulator.hs:202
-    d.act = ev.cand[k];
+    d.act = argmax_last_warp(sm.q, ev.cand, cand_lane, n, next_val);  // selectAction, Simulator.hs:202
     ncalls += is_end ? -1 : 1;  // gridStep, Simulator.hs:137-144
   }
   // backward scalars (Agent.hs:62-67,75,78)
@@ -1078,10 +1072,11 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
     // accFn1 = getAction (Simulator.hs:154-172)
     const VTree vt = q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r);
+    const int cand_lane = ev.cand[lane_id()];
     DCA_CLK(c1);
     cta_barrier();  // B2
     DCA_CLKB(c2);
-    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
+    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, cand_lane);
     DCA_CLK(c3);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
 #ifdef DCA_PHASE_CLOCK
@@ -1139,12 +1134,13 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     DCA_CLK(c0);
     const VTree vt = v_tree(sm);
     ev_prepare(sm, e, ev);
+    const int cand_lane = ev.cand[lane];
     DCA_CLK(c1);
     // (ev_env_push / ev_env_pop do not depend on the chosen channel and could run before B2; measured on
     //  B200 that makes this warp the late one at B2: 245 / 233 M events/s instead of 251 M)
     cta_barrier();  // B2
     DCA_CLKB(c2);
-    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
+    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, cand_lane);
     DCA_CLK(c3);
     const int pend_slot = ev_env_push(sm, e, type, cell, time, n > 0);       // Simulator.hs:101-128: new events
     const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
@@ -1269,11 +1265,11 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   __syncthreads();
   if (mode == 0) {
     float qb;
-    const int act = n > 0 ? ev.cand[argmax_last_warp(sm.q, n, qb)] : -1;
+    const int act = n > 0 ? argmax_last_warp(sm.q, ev.cand, ev.cand[lane], n, qb) : -1;
     if (threadIdx.x == 0) out->ch = act;
     return;
   }
-  const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls);
+  const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, ev.cand[lane]);
   if (wid == EVW) {
     if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);
   } else {
