@@ -141,6 +141,13 @@ __device__ __forceinline__ float rowdot2(const Row7& x, float2 w01, float2 w23, 
   const float e = __fmaf_rn(x.d, w6, acc.x);
   return __fadd_rn(e, acc.y);
 }
+// xor-shuffle whose position relative to the other volatile shuffles is kept by the compiler: the steps of
+// a butterfly then issue together (ptxas otherwise interleaves steps and lengthens the latency chain)
+__device__ __forceinline__ float shfl_xor_ordered(const float v, const int m) {
+  float r;
+  asm volatile("shfl.sync.bfly.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=f"(r) : "f"(v), "r"(m));
+  return r;
+}
 __device__ __forceinline__ uint2 badd(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ uint2 bsub(uint2 a, uint2 b) { return make_uint2(a.x - b.x, a.y - b.y); }
 
@@ -163,6 +170,7 @@ struct Lane {
   int xoff;           // byte offset of this lane's row in sm.x for slot 0 (+672 per slot)
   int woff;           // float offset of this lane's row in a half of sm.w for slot 0 (+336 per slot)
   bool rv;            // row valid
+  int pidx;           // index in sm.P of the plane sum this lane ends up with in dense_pass (-1: none)
 };
 // Roles rotate over the hardware warps from CTA to CTA (hardware warp w runs on SM sub-partition
 // w % 4): co-resident CTAs (block ids b, b + #SMs, b + 2 #SMs, ... in the first wave) then place their
@@ -187,6 +195,11 @@ __device__ __forceinline__ Lane make_lane() {
   const int rc = l.rv ? l.r : 6;
   l.xoff = l.g8 * PLANE + rc * ROWPAD;
   l.woff = (l.g8 * 7 + rc) * 4;
+  {  // see the reduce-scatter in dense_pass: row 0 -> slot 0, 1 -> 3, 2 -> 2, 3 -> 5, 4 -> 1, 5 -> 4 (rows 6, 7 repeat 2, 3)
+    const bool b0 = l.r & 1, b1 = l.r & 2, b2 = l.r & 4;
+    const int slot = b1 ? (b0 ? 5 : 2) : (b2 ? (b0 ? 4 : 1) : (b0 ? 3 : 0));
+    l.pidx = (l.r < 6 && l.vw < EVW && (slot < NSLOT - 1 || l.g8 != SLOTP - 1)) ? SLOTP * slot + l.g8 : -1;
+  }
   return l;
 }
 
@@ -287,18 +300,32 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     *clk_mid = clock64();
   }
 #endif
-  // plane sums: xor-butterfly 1,2,4 over the 8 lanes of a group, the six slots interleaved
-  // (the first three steps of the warp sum of x.wg ride along: independent shuffle chains)
-#pragma unroll
-  for (int s = 1; s < 8; s <<= 1) {
-#pragma unroll
-    for (int j = 0; j < NSLOT; ++j) rs[j] = __fadd_rn(rs[j], __shfl_xor_sync(0xffffffffu, rs[j], s));
-    rg_acc = __fadd_rn(rg_acc, __shfl_xor_sync(0xffffffffu, rg_acc, s));
-  }
-  if (l.r == 0) {
-#pragma unroll
-    for (int j = 0; j < NSLOT; ++j)
-      if (j < NSLOT - 1 || l.g8 != SLOTP - 1) sm.P[SLOTP * j + l.g8] = rs[j];
+  // plane sums: the xor-butterfly 1,2,4 over the 8 lanes (rows) of a group, for six slots at once as a
+  // reduce-scatter -- at every step a lane keeps half of its values and hands the other half to its
+  // partner, so the six sums cost 3 + 2 + 1 shuffles instead of 18.  Every sum is still formed as
+  // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+0)) (fp32 addition commutes), bit for bit the plane tree of the
+  // FAST order.  The first three steps of the warp sum of x.wg ride along.
+  {
+    const bool b0 = l.r & 1, b1 = l.r & 2, b2 = l.r & 4;
+    // step 1: even rows keep slots 0-2, odd rows slots 3-5
+    const float k0 = b0 ? rs[3] : rs[0], k1 = b0 ? rs[4] : rs[1], k2 = b0 ? rs[5] : rs[2];
+    const float s0 = b0 ? rs[0] : rs[3], s1 = b0 ? rs[1] : rs[4], s2 = b0 ? rs[2] : rs[5];
+    const float x0 = shfl_xor_ordered(s0, 1), x1 = shfl_xor_ordered(s1, 1), x2 = shfl_xor_ordered(s2, 1);
+    const float xg1 = shfl_xor_ordered(rg_acc, 1);
+    const float t0 = __fadd_rn(k0, x0), t1 = __fadd_rn(k1, x1), t2 = __fadd_rn(k2, x2);
+    rg_acc = __fadd_rn(rg_acc, xg1);
+    // step 2: rows 0,1,4,5 keep the first two of the three, rows 2,3,6,7 the third
+    const float y0 = shfl_xor_ordered(b1 ? t0 : t2, 2), y1 = shfl_xor_ordered(t1, 2);
+    const float xg2 = shfl_xor_ordered(rg_acc, 2);
+    const float u0 = __fadd_rn(b1 ? t2 : t0, y0), u1 = __fadd_rn(t1, y1);
+    rg_acc = __fadd_rn(rg_acc, xg2);
+    // step 3: rows 0,1 keep the first, rows 4,5 the second; rows 2,3 and 6,7 both finish the third
+    const float keep = (b2 && !b1) ? u1 : u0, send = (b2 || b1) ? u0 : u1;
+    const float z = shfl_xor_ordered(send, 4);
+    const float xg3 = shfl_xor_ordered(rg_acc, 4);
+    const float v = __fadd_rn(keep, z);
+    rg_acc = __fadd_rn(rg_acc, xg3);
+    if (l.pidx >= 0) sm.P[l.pidx] = v;
   }
   // warp sum of x.wg: xor-butterfly 1,2,4 (above), 8, 16
 #pragma unroll
@@ -1060,10 +1087,10 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
   cta_barrier();
   dense_pass<false>(sm, ag, l, -1, false, TdScalars{0.f, 0.f, 0.f, 0.f}, make_uint2(0, 0), make_uint2(0, 0));
   cta_barrier();  // B1
-#pragma unroll 1
 #ifdef DCA_PHASE_CLOCK
   unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
+#pragma unroll 1
   for (long long it = 0; it < a.max_events; ++it) {
     DCA_CLK(c0);
     const Ev& ev = sm.ev[it & 1];
