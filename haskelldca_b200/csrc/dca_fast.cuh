@@ -481,66 +481,101 @@ __device__ __forceinline__ VTree q_phase(SmemF& sm, const Lane& l, const Ev& ev,
 // NaNs follow the sequential right fold exactly.  Every warp computes it for itself.
 // cand_lane = cand[lane] (read before the barrier): the chosen channel rides along in the index
 // reduction, and the best value is rebuilt from the reduced key, so that nothing is loaded or
-// shuffled after the two reductions.  Returns the channel; qbest = q[k].
-__device__ __forceinline__ int argmax_last_warp(const float* q, const uint8_t* cand, int cand_lane, int n, float& qbest) {
+// shuffled after the two reductions.  The common case (n <= 32, no NaN) is branch-free; a NaN is
+// mapped to the largest key, so one warp-uniform test after the first reduction finds every
+// uncommon case.  Returns the channel; qbest = q[k].  (n == 0: the result is meaningless.)
+__device__ __noinline__ int argmax_uncommon(const float* q, const uint8_t* cand, int n, float& qbest) {
   const int lane = lane_id();
+  bool nan = false;
   float bq = -CUDART_INF_F;
   int bk = -1;
-  if (n <= 32) {
-    if (lane < n) { bq = q[lane]; bk = lane; }
-  } else {
 #pragma unroll 1
-    for (int k = lane; k < n; k += 32) {
-      const float v = q[k];
-      if (v >= bq || v != v) { bq = v; bk = k; cand_lane = cand[k]; }  // (a NaN is kept so that the slow path is taken)
-    }
+  for (int k = lane; k < n; k += 32) {
+    const float v = q[k];
+    nan |= v != v;
+    if (v >= bq) { bq = v; bk = k; }
   }
-  if (__any_sync(0xffffffffu, bq != bq)) {
-    int best = n - 1;
+  int best;
+  if (__any_sync(0xffffffffu, nan)) {  // the sequential right fold, NaNs included
+    best = n - 1;
 #pragma unroll 1
     for (int i = n - 2; i >= 0; --i)
       if (q[i] > q[best]) best = i;
-    qbest = q[best];
-    return cand[best];
+  } else {
+    uint32_t u = __float_as_uint(bq);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    if (bq == 0.0f) u = 0x80000000u;
+    if (bk < 0) u = 0u;
+    const uint32_t m = __reduce_max_sync(0xffffffffu, u);
+    best = __reduce_max_sync(0xffffffffu, (u == m) ? bk : -1);
   }
+  qbest = q[best];
+  return cand[best];
+}
+__device__ __forceinline__ int argmax_last_warp(const float* q, const uint8_t* cand, const int cand_lane, const int n,
+                                                float& qbest) {
+  const int lane = lane_id();
+  const float bq = q[lane];  // (lanes >= n read a stale value and are masked)
   // order-preserving map float -> uint32, then two warp reductions
   uint32_t u = __float_as_uint(bq);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
   if (bq == 0.0f) u = 0x80000000u;  // -0 == +0
-  if (bk < 0) u = 0u;
+  if (bq != bq) u = 0xFFFFFFFFu;    // above +inf: flags the uncommon path
+  if (lane >= n) u = 0u;
   const uint32_t m = __reduce_max_sync(0xffffffffu, u);
-  const int key = __reduce_max_sync(0xffffffffu, (u == m) ? ((bk << 8) | cand_lane) : -1);
+  const int key = __reduce_max_sync(0xffffffffu, (u == m) ? ((lane << 8) | cand_lane) : -1);
+  if (n > 32 || m == 0xFFFFFFFFu) return argmax_uncommon(q, cand, n, qbest);  // warp-uniform
   // the inverse map gives q[k] bit for bit, except that a best value of -0 comes back as +0: it is only
   // ever added to reward - avgR, which is never -0, so the sum is the same
   qbest = __uint_as_float((m & 0x80000000u) ? (m & 0x7FFFFFFFu) : ~m);
   return key & 0xFF;
 }
 
-// what every thread derives from the Q phase: the action and the TD scalars
+// what every thread derives from the Q phase: the action and the TD scalars.  Everything that does not
+// depend on the q values is prepared BEFORE the barrier that publishes them (decide_prepare); after it
+// only argmax, three dependent flops to c * td, and the learning-rate products remain.
 struct Decision {
   int act;
   float tderr;
   TdScalars td;
 };
-__device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const VTree& vt, int n, bool is_end,
-                                           float& avgR, int& ncalls, const int cand_lane) {
-  const float alpha_net = sm.alpha_net, alpha_avg = sm.alpha_avg, alpha_grad = sm.alpha_grad;
+struct DecidePrep {
+  int cand_lane;  // cand[lane]
+  int ncalls1;    // calls in progress after this event if a channel is chosen (gridStep, Simulator.hs:137-144)
+  float base;     // reward - avgR for that reward                       (Agent.hs:65)
+  float c;        // -2 alphaNet                                         (Agent.hs:67)
+  float cavg, ncdot;
+  float alpha_avg, alpha_grad;
+};
+__device__ __forceinline__ DecidePrep decide_prepare(const SmemF& sm, const Ev& ev, const VTree& vt, const int n,
+                                                     const bool is_end, const float avgR, const int ncalls) {
+  DecidePrep p;
+  p.cand_lane = ev.cand[lane_id()];
+  p.ncalls1 = n > 0 ? ncalls + (is_end ? -1 : 1) : ncalls;
+  const float reward = (float)p.ncalls1;  // boolSum nextGrid
+  p.base = __fsub_rn(reward, avgR);
+  p.c = __fmul_rn(-2.0f, sm.alpha_net);
+  p.cavg = __fmul_rn(p.c, avgR);
+  p.ncdot = -__fmul_rn(p.c, vt.dotg);
+  p.alpha_avg = sm.alpha_avg;
+  p.alpha_grad = sm.alpha_grad;
+  return p;
+}
+__device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const VTree& vt, const DecidePrep& p,
+                                           const int n, float& avgR, int& ncalls) {
   Decision d;
-  d.act = -1;
-  float next_val = vt.val;  // no action: nextFrep = frep (Simulator.hs:170-171)
-  if (n > 0) {
-    d.act = argmax_last_warp(sm.q, ev.cand, cand_lane, n, next_val);  // selectAction, Simulator.hs:202
-    ncalls += is_end ? -1 : 1;  // gridStep, Simulator.hs:137-144
-  }
+  float qbest;
+  const int act = argmax_last_warp(sm.q, ev.cand, p.cand_lane, n, qbest);  // selectAction, Simulator.hs:202
+  d.act = n > 0 ? act : -1;
+  const float next_val = n > 0 ? qbest : vt.val;  // no action: nextFrep = frep (Simulator.hs:170-171)
+  ncalls = p.ncalls1;
   // backward scalars (Agent.hs:62-67,75,78)
-  const float reward = (float)ncalls;  // boolSum nextGrid
-  d.tderr = __fsub_rn(__fadd_rn(__fsub_rn(reward, avgR), next_val), vt.val);
-  const float c = __fmul_rn(-2.0f, alpha_net);
-  d.td.ctd = __fmul_rn(c, d.tderr);
-  d.td.cavg = __fmul_rn(c, avgR);
-  d.td.ncdot = -__fmul_rn(c, vt.dotg);
-  d.td.sg = __fmul_rn(alpha_grad, __fsub_rn(d.tderr, vt.dotg));
-  avgR = __fadd_rn(avgR, __fmul_rn(alpha_avg, d.tderr));
+  d.tderr = __fsub_rn(__fadd_rn(p.base, next_val), vt.val);
+  d.td.ctd = __fmul_rn(p.c, d.tderr);
+  d.td.cavg = p.cavg;
+  d.td.ncdot = p.ncdot;
+  d.td.sg = __fmul_rn(p.alpha_grad, __fsub_rn(d.tderr, vt.dotg));
+  avgR = __fadd_rn(avgR, __fmul_rn(p.alpha_avg, d.tderr));
   return d;
 }
 
@@ -1099,11 +1134,11 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
     // accFn1 = getAction (Simulator.hs:154-172)
     const VTree vt = q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r);
-    const int cand_lane = ev.cand[lane_id()];
+    const DecidePrep dp = decide_prepare(sm, ev, vt, n, is_end, avgR, ncalls);
     DCA_CLK(c1);
     cta_barrier();  // B2
     DCA_CLKB(c2);
-    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, cand_lane);
+    const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
 #ifdef DCA_PHASE_CLOCK
@@ -1161,13 +1196,13 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     DCA_CLK(c0);
     const VTree vt = v_tree(sm);
     ev_prepare(sm, e, ev);
-    const int cand_lane = ev.cand[lane];
+    const DecidePrep dp = decide_prepare(sm, ev, vt, n, is_end, avgR, ncalls);
     DCA_CLK(c1);
     // (ev_env_push / ev_env_pop do not depend on the chosen channel and could run before B2; measured on
     //  B200 that makes this warp the late one at B2: 245 / 233 M events/s instead of 251 M)
     cta_barrier();  // B2
     DCA_CLKB(c2);
-    const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, cand_lane);
+    const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
     const int pend_slot = ev_env_push(sm, e, type, cell, time, n > 0);       // Simulator.hs:101-128: new events
     const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
@@ -1296,7 +1331,7 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
     if (threadIdx.x == 0) out->ch = act;
     return;
   }
-  const Decision d = decide(sm, ev, vt, n, is_end, avgR, ncalls, ev.cand[lane]);
+  const Decision d = decide(sm, ev, vt, decide_prepare(sm, ev, vt, n, is_end, avgR, ncalls), n, avgR, ncalls);
   if (wid == EVW) {
     if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);
   } else {
