@@ -516,10 +516,9 @@ __device__ __forceinline__ int argmax_last_warp(const float* q, const uint8_t* c
                                                 float& qbest) {
   const int lane = lane_id();
   const float bq = q[lane];  // (lanes >= n read a stale value and are masked)
-  // order-preserving map float -> uint32, then two warp reductions
-  uint32_t u = __float_as_uint(bq);
-  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  if (bq == 0.0f) u = 0x80000000u;  // -0 == +0
+  // order-preserving map float -> uint32 (shifts and xors: no predicate latency), then two warp reductions
+  const uint32_t bits = __float_as_uint(__fadd_rn(bq, 0.0f));                  // -0 -> +0
+  uint32_t u = bits ^ ((uint32_t)((int32_t)bits >> 31) | 0x80000000u);         // negative: ~bits, else bits | sign
   if (bq != bq) u = 0xFFFFFFFFu;    // above +inf: flags the uncommon path
   if (lane >= n) u = 0u;
   const uint32_t m = __reduce_max_sync(0xffffffffu, u);
@@ -527,7 +526,7 @@ __device__ __forceinline__ int argmax_last_warp(const float* q, const uint8_t* c
   if (n > 32 || m == 0xFFFFFFFFu) return argmax_uncommon(q, cand, n, qbest);  // warp-uniform
   // the inverse map gives q[k] bit for bit, except that a best value of -0 comes back as +0: it is only
   // ever added to reward - avgR, which is never -0, so the sum is the same
-  qbest = __uint_as_float((m & 0x80000000u) ? (m & 0x7FFFFFFFu) : ~m);
+  qbest = __uint_as_float(m ^ ~((uint32_t)((int32_t)m >> 31) & 0x7FFFFFFFu));
   return key & 0xFF;
 }
 
