@@ -546,8 +546,10 @@ struct DecidePrep {
   float cavg, ncdot;
   float alpha_avg, alpha_grad;
 };
-__device__ __forceinline__ DecidePrep decide_prepare(const SmemF& sm, const Ev& ev, const VTree& vt, const int n,
-                                                     const bool is_end, const float avgR, const int ncalls) {
+// (called before the candidate evaluation, so that its loads are in flight early; ncdot follows when
+//  x.wGradCorr is known)
+__device__ __forceinline__ DecidePrep decide_prepare(const SmemF& sm, const Ev& ev, const int n, const bool is_end,
+                                                     const float avgR, const int ncalls) {
   DecidePrep p;
   p.cand_lane = ev.cand[lane_id()];
   p.ncalls1 = n > 0 ? ncalls + (is_end ? -1 : 1) : ncalls;
@@ -555,7 +557,7 @@ __device__ __forceinline__ DecidePrep decide_prepare(const SmemF& sm, const Ev& 
   p.base = __fsub_rn(reward, avgR);
   p.c = __fmul_rn(-2.0f, sm.alpha_net);
   p.cavg = __fmul_rn(p.c, avgR);
-  p.ncdot = -__fmul_rn(p.c, vt.dotg);
+  p.ncdot = 0.0f;
   p.alpha_avg = sm.alpha_avg;
   p.alpha_grad = sm.alpha_grad;
   return p;
@@ -1132,8 +1134,9 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const bool is_end = ev.type == EV_END;
     const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
     // accFn1 = getAction (Simulator.hs:154-172)
+    DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
     const VTree vt = q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r);
-    const DecidePrep dp = decide_prepare(sm, ev, vt, n, is_end, avgR, ncalls);
+    dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
     DCA_CLK(c1);
     cta_barrier();  // B2
     DCA_CLKB(c2);
@@ -1193,9 +1196,10 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const double time = ev.time;
     const bool is_end = type == EV_END;
     DCA_CLK(c0);
+    DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
     const VTree vt = v_tree(sm);
+    dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
     ev_prepare(sm, e, ev);
-    const DecidePrep dp = decide_prepare(sm, ev, vt, n, is_end, avgR, ncalls);
     DCA_CLK(c1);
     // (ev_env_push / ev_env_pop do not depend on the chosen channel and could run before B2; measured on
     //  B200 that makes this warp the late one at B2: 245 / 233 M events/s instead of 251 M)
@@ -1330,7 +1334,9 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
     if (threadIdx.x == 0) out->ch = act;
     return;
   }
-  const Decision d = decide(sm, ev, vt, decide_prepare(sm, ev, vt, n, is_end, avgR, ncalls), n, avgR, ncalls);
+  DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
+  dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
+  const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
   if (wid == EVW) {
     if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);
   } else {
