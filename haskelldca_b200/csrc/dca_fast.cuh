@@ -221,6 +221,17 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
   const float sgn = is_end ? -1.0f : 1.0f;
   bool own_act = false;                      // does this lane own a row of plane `act`?
   (void)dm; (void)sgn;
+  // The warp that owns plane 70 (n_elig) also moves cnt2[act] to the afterstate; it does so up front, where
+  // the load latency hides behind the first slot: cg = the cells of N2 u {cell} where `act` is eligible on
+  // grid' (cnt2 == 0, or == 1 when the call at `cell` ends).  The four groups hold the same row: same values.
+  uint2 cg = make_uint2(0, 0);
+  if (UPDATE && wid == 2 && act >= 0) {      // warp-uniform
+    const int co = act * PLANE + (l.rv ? l.r : 6) * ROWPAD;
+    const uint2 cr = *reinterpret_cast<const uint2*>(&sm.cnt2[co]);
+    const uint32_t want = is_end ? 1u : 0u;
+    cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
+    *reinterpret_cast<uint2*>(&sm.cnt2[co]) = is_end ? bsub(cr, n2b_r) : badd(cr, n2b_r);
+  }
 #pragma unroll
   for (int j = 0; j < NSLOT; ++j) {
     const bool last = j == NSLOT - 1;
@@ -246,17 +257,11 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
       xn.b = __ffma2_rn(f2(sa), dm.b, xo.b);
       xn.c = __ffma2_rn(f2(sa), dm.c, xo.c);
       xn.d = __fmaf_rn(sa, dm.d, xo.d);
-      if (last && wid == 2 && act >= 0) {  // warp-uniform: the owners of plane 70 (n_elig) and of cnt2[act]
+      if (last && wid == 2 && act >= 0) {  // warp-uniform: the owners of plane 70 (n_elig)
         if (f == NCH) {  // (the shadow lanes -- row 7, group 11 -- compute and store the same values as their originals)
-          const int co = act * PLANE + (l.rv ? l.r : 6) * ROWPAD;
-          const uint2 cr = *reinterpret_cast<const uint2*>(&sm.cnt2[co]);
-          const uint32_t want = is_end ? 1u : 0u;
-          // cells of N2 u {cell} where `act` is eligible on grid' (cnt2 == 0, or == 1 when the call at cell ends)
-          const uint2 cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
           const uint2 eb = is_end ? badd(xb, cg) : bsub(xb, cg);
           xn = cvt_row(eb);
           *reinterpret_cast<uint2*>(&sm.x[xo_]) = eb;
-          *reinterpret_cast<uint2*>(&sm.cnt2[co]) = is_end ? bsub(cr, n2b_r) : badd(cr, n2b_r);
         }
       }
 #define DCA_UPD2(W, G, XN, XO)                                            \
