@@ -172,16 +172,19 @@ struct Lane {
   bool rv;            // row valid
   int pidx;           // index in sm.P of the plane sum this lane ends up with in dense_pass (-1: none)
 };
-// Roles rotate over the hardware warps from CTA to CTA (hardware warp w runs on SM sub-partition
-// w % 4): co-resident CTAs (block ids b, b + #SMs, b + 2 #SMs, ... in the first wave) then place their
-// light event warps on four different schedulers instead of all on the same one.
+// Which hardware warp plays the event role.  The hardware already spreads the warps of the four CTAs of
+// an SM over the four sub-partitions: the CTA in slot k gets warp slots [4k + (k + w) % 4] (measured:
+// [0 1 2 3], [5 6 7 4], [10 11 8 9], [15 12 13 14]; tools/microbench/placement.cu), so CTAs that share an
+// SM must use the SAME role assignment for their event warps to land on four different schedulers
+// (measured on one resident wave: 277 M events/s with equal assignments, 267-272 M with mixed ones).
+// The assignment therefore only changes from wave to wave (block ids of one wave share it).
 __device__ __forceinline__ int role_rotation() {
 #ifdef DCA_NO_ROTATE_ROLES
   return 0;
 #else
   unsigned nsm;
   asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-  return (int)((blockIdx.x / nsm) & 3u);
+  return (int)((blockIdx.x / (4u * nsm)) & 3u);
 #endif
 }
 __device__ __forceinline__ int virtual_tid() { return (int)((threadIdx.x + 32u * (unsigned)role_rotation()) & 127u); }
