@@ -1028,6 +1028,9 @@ int dca_allreduce_stats(dca_handle** handles, int32_t n, int64_t out[10]) {
 }  // extern "C"
 
 #ifdef DCA_PHASE_CLOCK
+extern "C" int dca_debug_cta(unsigned long long* out, int n_blocks) {
+  return cudaMemcpyFromSymbol(out, dca::fast::g_cta, sizeof(unsigned long long) * 2 * (size_t)n_blocks) == cudaSuccess ? 0 : -1;
+}
 extern "C" int dca_debug_phase(unsigned long long* out, int reset) {
   if (cudaMemcpyFromSymbol(out, dca::fast::g_phase, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
   if (reset) {

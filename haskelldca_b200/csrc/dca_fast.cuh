@@ -83,6 +83,7 @@ __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" 
 
 #ifdef DCA_PHASE_CLOCK  // development only: cycles per role (virtual warp) and phase, summed over CTAs and events
 __device__ unsigned long long g_phase[4][8];
+__device__ unsigned long long g_cta[8192][2];  // per block: cycles in the run kernel, SM id
 #define DCA_CLK(v) const long long v = clock64()
 // after a barrier: BAR.SYNC.DEFER_BLOCKING lets the warp run on to its first shared-memory access, so wait for one
 #define DCA_CLKB(v)                                            \
@@ -1293,8 +1294,19 @@ __global__ void __launch_bounds__(NT, DCA_MIN_CTAS) k_run_fast(RunArgs a) {
   if (rep >= a.n_replicas) return;
   RepState* g = a.states + rep;
   if (!g->initialized || g->status != ST_RUNNING) return;  // uniform
+#ifdef DCA_PHASE_CLOCK
+  const long long cta_t0 = clock64();
+#endif
   if ((virtual_tid() >> 5) == EVW) event_main<TRACE>(sm, a, g, rep);
   else agent_main<TRACE>(sm, a, g);
+#ifdef DCA_PHASE_CLOCK
+  if (threadIdx.x == 0 && blockIdx.x < 8192) {
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_cta[blockIdx.x][0] = (unsigned long long)(clock64() - cta_t0);
+    g_cta[blockIdx.x][1] = smid;
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------
