@@ -3,9 +3,11 @@
 // One CTA of 128 threads per replica, resident for the whole launch:
 //   warps 0-2  "agent" threads (96): the value function and the TDC update.
 //              Lane r (0..6; lane 7 idles) of 8-lane group g (0..11) owns row r of
-//              feature plane f = 12*slot + g for slot = 0..5.  wGradCorr lives in
-//              those threads' registers (6 x 7 floats), wNet in shared memory (the
-//              afterstate evaluation needs it with a flexible lane mapping).
+//              feature plane f = 12*slot + g for slot = 0..5.  wGradCorr (6 x 7 floats
+//              per lane, never read by another thread) lives in Blackwell tensor memory
+//              used as a per-thread scratchpad (tcgen05.ld / st; or in registers with
+//              DCA_WG_REGS), wNet in shared memory (the afterstate evaluation needs it
+//              with a flexible lane mapping).  96 registers, 43.6 KB -> 5 CTAs per SM.
 //   warp 3     "event" warp: event queue, random numbers, statistics, grid bits,
 //              candidate channels, stop rules (environmentStep, src/Simulator.hs:101-134).
 //
@@ -44,6 +46,20 @@ constexpr int NBLK = 22;      // queue blocks of 32 slots
 constexpr int QCAPS = NBLK * 32;  // 704 >= QCAP: whole blocks can be scanned
 static_assert(QCAPS >= QCAP, "queue blocks");
 
+// Where wGradCorr lives (see struct Agent) and, with it, how many CTAs share an SM.
+#if !defined(DCA_WG_REGS) && !defined(DCA_WG_TMEM)
+#define DCA_WG_TMEM  // measured on B200: 294.4 vs 287.9 M events/s (4096 replicas), 299.6 vs 292.1 M (5920)
+#endif
+// With wGradCorr in registers: 4 CTAs per SM (128 registers/thread, no spills) beat 5 (96 registers,
+// spills): 287 vs 258 M events/s on B200.  With wGradCorr in tensor memory the kernel fits 96 registers.
+#ifndef DCA_MIN_CTAS
+#ifdef DCA_WG_TMEM
+#define DCA_MIN_CTAS 5
+#else
+#define DCA_MIN_CTAS 4
+#endif
+#endif
+
 struct Ev {  // an event and its candidate set (double-buffered: the event warp writes
              // the next one while the agents still use the current one)
   double time;
@@ -72,6 +88,7 @@ struct alignas(16) SmemF {
   float Wg[4];              // per-warp partial sums of x.wGradCorr
   float alpha_net, alpha_avg, alpha_grad;  // alphaNet, alphaAvg, alphaGrad of this replica
   int status;
+  uint32_t tmem_base, pad_[3];  // tensor-memory columns of this CTA (wGradCorr, DCA_WG_TMEM)
 };
 static_assert(sizeof(SmemF) % 16 == 0, "SmemF size");
 static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && offsetof(SmemF, grid) % 16 == 0 &&
@@ -155,10 +172,79 @@ __device__ __forceinline__ uint2 bsub(uint2 a, uint2 b) { return make_uint2(a.x 
 // ---------------------------------------------------------------------------
 // Agent side
 // ---------------------------------------------------------------------------
-struct Agent {       // per-thread registers of an agent thread
-  float2 g01[NSLOT], g23[NSLOT], g45[NSLOT];  // wGradCorr rows of this lane, one per slot
-  float g6[NSLOT];
+// wGradCorr of an agent lane: 6 rows x 7 floats that no other thread ever reads.
+//  * DCA_WG_REGS: 42 registers per thread, which caps the kernel at 4 CTAs per SM;
+//  * DCA_WG_TMEM (default): Blackwell tensor memory used as a per-thread scratchpad -- lane l of hardware warp w
+//    owns TMEM lane 32 (w % 4) + l, slot j sits in columns 8 j .. 8 j + 6 of the CTA's 64 columns
+//    (tcgen05.ld / st .32x32b.x8: one row per instruction, ~12 cycles), and the kernel fits 5 CTAs per SM.
+struct WgRow {
+  float2 g01, g23, g45;
+  float g6;
 };
+#ifdef DCA_WG_TMEM
+struct Agent {
+  uint32_t taddr;  // TMEM address (lane quarter of this warp, first column of the CTA)
+};
+struct WgRegs {    // a row in flight: valid after wg_wait
+  uint32_t r[8];
+};
+__device__ __forceinline__ WgRegs wg_get(const Agent& ag, const int j) {
+  WgRegs v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
+               : "r"(ag.taddr + 8u * (uint32_t)j));
+  return v;
+}
+__device__ __forceinline__ WgRow wg_wait(WgRegs& v) {  // (the registers are operands so that no use moves above the wait)
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v.r[0]), "+r"(v.r[1]), "+r"(v.r[2]), "+r"(v.r[3]), "+r"(v.r[4]), "+r"(v.r[5]), "+r"(v.r[6]), "+r"(v.r[7]));
+  WgRow g;
+  g.g01 = make_float2(__uint_as_float(v.r[0]), __uint_as_float(v.r[1]));
+  g.g23 = make_float2(__uint_as_float(v.r[2]), __uint_as_float(v.r[3]));
+  g.g45 = make_float2(__uint_as_float(v.r[4]), __uint_as_float(v.r[5]));
+  g.g6 = __uint_as_float(v.r[6]);
+  return g;
+}
+__device__ __forceinline__ void wg_put(Agent& ag, const int j, const WgRow& g) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "r"(ag.taddr + 8u * (uint32_t)j), "r"(__float_as_uint(g.g01.x)), "r"(__float_as_uint(g.g01.y)),
+                  "r"(__float_as_uint(g.g23.x)), "r"(__float_as_uint(g.g23.y)), "r"(__float_as_uint(g.g45.x)),
+                  "r"(__float_as_uint(g.g45.y)), "r"(__float_as_uint(g.g6)), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void wg_commit() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+constexpr uint32_t TMEM_COLS = 64;
+// CTA-wide: hardware warp 0 allocates, everybody learns the base
+__device__ __forceinline__ void tmem_open(SmemF& sm, Agent& ag) {
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(&sm.tmem_base)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  ag.taddr = sm.tmem_base + ((threadIdx.x >> 5) * 32u << 16);
+}
+__device__ __forceinline__ void tmem_close(SmemF& sm) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(sm.tmem_base), "r"(TMEM_COLS) : "memory");
+}
+#else
+struct Agent {       // per-thread registers of an agent thread
+  WgRow g[NSLOT];    // wGradCorr rows of this lane, one per slot
+};
+struct WgRegs {
+  WgRow g;
+};
+__device__ __forceinline__ WgRegs wg_get(const Agent& ag, const int j) { return WgRegs{ag.g[j]}; }
+__device__ __forceinline__ WgRow wg_wait(WgRegs& v) { return v.g; }
+__device__ __forceinline__ void wg_put(Agent& ag, const int j, const WgRow& g) { ag.g[j] = g; }
+__device__ __forceinline__ void wg_commit() {}
+__device__ __forceinline__ void tmem_open(SmemF&, Agent&) {}
+__device__ __forceinline__ void tmem_close(SmemF&) {}
+#endif
 
 struct TdScalars {
   float ctd, cavg, ncdot, sg;
@@ -185,7 +271,7 @@ __device__ __forceinline__ int role_rotation() {
 #else
   unsigned nsm;
   asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
-  return (int)((blockIdx.x / (4u * nsm)) & 3u);
+  return (int)((blockIdx.x / ((unsigned)DCA_MIN_CTAS * nsm)) & 3u);
 #endif
 }
 __device__ __forceinline__ int virtual_tid() { return (int)((threadIdx.x + 32u * (unsigned)role_rotation()) & 127u); }
@@ -248,9 +334,11 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     const uint2 xb = *reinterpret_cast<const uint2*>(&sm.x[xo_]);
     const float4 wa = *reinterpret_cast<const float4*>(&sm.w[0][wo_]);
     const float4 wb = *reinterpret_cast<const float4*>(&sm.w[1][wo_]);
+    WgRegs gin = wg_get(ag, j);
     float2 w01 = make_float2(wa.x, wa.y), w23 = make_float2(wa.z, wa.w), w45 = make_float2(wb.x, wb.y);
     float w6 = wb.z;
     const Row7 xo = cvt_row(xb);
+    WgRow G = wg_wait(gin);
     Row7 xn = xo;
     if (UPDATE) {
       // x' = x + s * [cell in N4 \ {cell}], s = +-1 on plane `act` and 0 elsewhere: small integers, exact in
@@ -275,15 +363,16 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     W = __ffma2_rn(g_, f2(-1.0f), W);                                     \
     G = __ffma2_rn(f2(td.sg), XO, G);                                     \
   }
-      DCA_UPD2(w01, ag.g01[j], xn.a, xo.a)
-      DCA_UPD2(w23, ag.g23[j], xn.b, xo.b)
-      DCA_UPD2(w45, ag.g45[j], xn.c, xo.c)
+      DCA_UPD2(w01, G.g01, xn.a, xo.a)
+      DCA_UPD2(w23, G.g23, xn.b, xo.b)
+      DCA_UPD2(w45, G.g45, xn.c, xo.c)
 #undef DCA_UPD2
       {
         const float t_ = __fmaf_rn(td.ctd, xo.d, td.cavg);
         const float g_ = __fmaf_rn(td.ncdot, xn.d, t_);
         w6 = __fsub_rn(w6, g_);
-        ag.g6[j] = __fmaf_rn(td.sg, xo.d, ag.g6[j]);
+        G.g6 = __fmaf_rn(td.sg, xo.d, G.g6);
+        wg_put(ag, j, G);
       }
       // unconditional: a shadow lane (row 7 -> row 6, group 11 in the last slot -> plane 70) holds the same
       // x, w and wGradCorr as its original and stores the same values to the same address
@@ -291,7 +380,7 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
       *reinterpret_cast<float4*>(&sm.w[1][wo_]) = make_float4(w45.x, w45.y, w6, 0.0f);
     }
     rs[j] = valid ? rowdot2(xn, w01, w23, w45, w6) : 0.0f;
-    const float rg = rowdot2(xn, ag.g01[j], ag.g23[j], ag.g45[j], ag.g6[j]);
+    const float rg = rowdot2(xn, G.g01, G.g23, G.g45, G.g6);
     if (j == 0) rg_acc = l.rv ? rg : 0.0f;
     else if (valid) rg_acc = __fadd_rn(rg_acc, rg);
   }
@@ -1074,21 +1163,25 @@ __device__ __forceinline__ void load_wg(Agent& ag, const RepState* g, const Lane
     if (f > NCH) f = NCH;
     const float4* src = reinterpret_cast<const float4*>(&g->wg[f * PLANE + rc * ROWPAD]);
     const float4 a = src[0], b = src[1];
-    ag.g01[j] = make_float2(a.x, a.y);
-    ag.g23[j] = make_float2(a.z, a.w);
-    ag.g45[j] = make_float2(b.x, b.y);
-    ag.g6[j] = b.z;
+    WgRow G;
+    G.g01 = make_float2(a.x, a.y);
+    G.g23 = make_float2(a.z, a.w);
+    G.g45 = make_float2(b.x, b.y);
+    G.g6 = b.z;
+    wg_put(ag, j, G);
   }
+  wg_commit();
 }
 __device__ __forceinline__ void store_wg(const Agent& ag, RepState* g, const Lane& l) {
-  if (!l.rv) return;
 #pragma unroll
-  for (int j = 0; j < NSLOT; ++j) {
+  for (int j = 0; j < NSLOT; ++j) {  // (warp-uniform: the tensor-memory loads are warp-wide)
+    WgRegs gin = wg_get(ag, j);
+    const WgRow G = wg_wait(gin);
     const int f = SLOTP * j + l.g8;
-    if (f <= NCH) {
+    if (l.rv && f <= NCH) {
       float4* dst = reinterpret_cast<float4*>(&g->wg[f * PLANE + l.r * ROWPAD]);
-      dst[0] = make_float4(ag.g01[j].x, ag.g01[j].y, ag.g23[j].x, ag.g23[j].y);
-      dst[1] = make_float4(ag.g45[j].x, ag.g45[j].y, ag.g6[j], 0.0f);
+      dst[0] = make_float4(G.g01.x, G.g01.y, G.g23.x, G.g23.y);
+      dst[1] = make_float4(G.g45.x, G.g45.y, G.g6, 0.0f);
     }
   }
 }
@@ -1120,11 +1213,10 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
 // event warp sees the afterstate before it hashes / verifies it.
 // ---------------------------------------------------------------------------
 template <bool TRACE>
-__device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState* g) {
+__device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState* g, Agent& ag) {
   const bool sync_end = TRACE || a.verify_rc || a.verify_nb;
   const Lane l = make_lane();
   const int rc = l.rv ? l.r : 6;
-  Agent ag;
   stage_in(sm, g);
   load_wg(ag, g, l);
   float avgR = g->avg_reward;
@@ -1281,11 +1373,6 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   }
 }
 
-// 4 CTAs per SM (128 registers/thread, no spills) beat 5 (96 registers, spills and rematerialised
-// lane constants in the agent loop): 236 vs 206 M events/s on B200.
-#ifndef DCA_MIN_CTAS
-#define DCA_MIN_CTAS 4
-#endif
 template <bool TRACE>
 __global__ void __launch_bounds__(NT, DCA_MIN_CTAS) k_run_fast(RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1297,8 +1384,11 @@ __global__ void __launch_bounds__(NT, DCA_MIN_CTAS) k_run_fast(RunArgs a) {
 #ifdef DCA_PHASE_CLOCK
   const long long cta_t0 = clock64();
 #endif
+  Agent ag;
+  tmem_open(sm, ag);
   if ((virtual_tid() >> 5) == EVW) event_main<TRACE>(sm, a, g, rep);
-  else agent_main<TRACE>(sm, a, g);
+  else agent_main<TRACE>(sm, a, g, ag);
+  tmem_close(sm);
 #ifdef DCA_PHASE_CLOCK
   if (threadIdx.x == 0 && blockIdx.x < 8192) {
     unsigned smid;
@@ -1325,6 +1415,7 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   const int wid = l.vw, lane = lane_id();
   const int rc = l.rv ? l.r : 6;
   Agent ag;
+  tmem_open(sm, ag);
   stage_in(sm, g);
   if (wid != EVW) load_wg(ag, g, l);
   float avgR = g->avg_reward;
@@ -1352,6 +1443,7 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
     float qb;
     const int act = n > 0 ? argmax_last_warp(sm.q, ev.cand, ev.cand[lane], n, qb) : -1;
     if (threadIdx.x == 0) out->ch = act;
+    tmem_close(sm);
     return;
   }
   DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
@@ -1383,6 +1475,7 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
     out->loss_is_nan = (d.tderr != d.tderr) ? 1 : 0;
     out->reward = ncalls;
   }
+  tmem_close(sm);
 }
 
 }  // namespace fast

@@ -1,6 +1,7 @@
 // Development micro-benchmark: the agents' dense pass / evaluation phase of dca_fast.cuh in isolation
 // (cycles per pass per warp at 1..4 CTAs per SM).
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -I../../haskelldca_b200/csrc -o dense_bench dense_bench.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -DDCA_WG_REGS -I../../haskelldca_b200/csrc -o dense_bench dense_bench.cu
+// (wGradCorr in registers: the tensor-memory variant needs the allocation the run kernel does)
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "dca_fast.cuh"
@@ -27,7 +28,7 @@ __global__ void __launch_bounds__(NT, 4) kd(int iters, long long* cyc, float* ou
   const int rc = l.rv ? l.r : 6;
   Agent ag;
 #pragma unroll
-  for (int j = 0; j < NSLOT; ++j) { ag.g01[j] = ag.g23[j] = ag.g45[j] = make_float2(1e-4f * j, 2e-4f); ag.g6[j] = 1e-4f; }
+  for (int j = 0; j < NSLOT; ++j) { ag.g[j].g01 = ag.g[j].g23 = ag.g[j].g45 = make_float2(1e-4f * j, 2e-4f); ag.g[j].g6 = 1e-4f; }
   const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
   TdScalars td{1e-7f, 2e-7f, -1e-7f, 1e-8f};
   int act = act0;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(NT, 4) kd(int iters, long long* cyc, float* ou
   const long long t1 = clock64();
   float s = acc + td.ctd;
 #pragma unroll
-  for (int j = 0; j < NSLOT; ++j) s += ag.g01[j].x + ag.g6[j];
+  for (int j = 0; j < NSLOT; ++j) s += ag.g[j].g01.x + ag.g[j].g6;
   out[blockIdx.x * NT + threadIdx.x] = s;
   if (threadIdx.x % 32 == 0 && blockIdx.x == 0) cyc[threadIdx.x / 32] = t1 - t0;
 }
