@@ -429,6 +429,7 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
 #pragma unroll
   for (int s = 8; s < 32; s <<= 1) rg_acc = __fadd_rn(rg_acc, __shfl_xor_sync(0xffffffffu, rg_acc, s));
   if (lane_id() == 0) sm.Wg[wid] = rg_acc;
+  if (UPDATE) wg_commit();  // the rows written above are read again by the next pass
 }
 
 // V(s) = x.w from the plane sums; every lane keeps the butterfly siblings it
