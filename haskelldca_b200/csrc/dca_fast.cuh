@@ -88,7 +88,9 @@ struct alignas(16) SmemF {
   float Wg[4];              // per-warp partial sums of x.wGradCorr
   float alpha_net, alpha_avg, alpha_grad;  // alphaNet, alphaAvg, alphaGrad of this replica
   int status;
-  uint32_t tmem_base, pad_[3];  // tensor-memory columns of this CTA (wGradCorr, DCA_WG_TMEM)
+  uint32_t tmem_base;       // tensor-memory columns of this CTA (wGradCorr, DCA_WG_TMEM)
+  float v_pub;              // V(s) of the current event, published by the agents before the argmax barrier
+  uint32_t pad_[2];
 };
 static_assert(sizeof(SmemF) % 16 == 0, "SmemF size");
 static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && offsetof(SmemF, grid) % 16 == 0 &&
@@ -101,15 +103,15 @@ __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" 
 #ifdef DCA_PHASE_CLOCK  // development only: cycles per role (virtual warp) and phase, summed over CTAs and events
 __device__ unsigned long long g_phase[4][8];
 __device__ unsigned long long g_cta[8192][2];  // per block: cycles in the run kernel, SM id
-#define DCA_CLK(v) const long long v = clock64()
+#define DCA_CLK(v) const unsigned v = (unsigned)clock64()  /* 32-bit stamps and sums: few registers */
 // after a barrier: BAR.SYNC.DEFER_BLOCKING lets the warp run on to its first shared-memory access, so wait for one
 #define DCA_CLKB(v)                                            \
   {                                                            \
     const int s_ = *(volatile int*)&sm.status;                 \
     if (s_ == 0x7ffffff0) asm volatile("trap;");               \
   }                                                            \
-  const long long v = clock64()
-#define DCA_ACC(i, a, b) ph[i] += (unsigned long long)((b) - (a))
+  const unsigned v = (unsigned)clock64()
+#define DCA_ACC(i, a, b) ph[i] += (b) - (a)
 #else
 #define DCA_CLK(v)
 #define DCA_CLKB(v)
@@ -302,8 +304,7 @@ __device__ __forceinline__ Lane make_lane() {
 // Without UPDATE only the sums of the current state are formed.
 template <bool UPDATE>
 __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, const int act, const bool is_end,
-                                           const TdScalars td, const uint2 n4b_r, const uint2 n2b_r,
-                                           long long* clk_mid = nullptr) {
+                                           const TdScalars td, const uint2 n4b_r, const uint2 n2b_r) {
   const int wid = l.vw;
   float rs[NSLOT];
   float rg_acc = 0.0f;
@@ -389,15 +390,6 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     const uint2 xb_act = *xp;
     *xp = is_end ? bsub(xb_act, n4b_r) : badd(xb_act, n4b_r);
   }
-#ifdef DCA_PHASE_CLOCK
-  if (clk_mid) {  // wait for the row sums, then stamp
-    float s_ = rg_acc;
-#pragma unroll
-    for (int j = 0; j < NSLOT; ++j) s_ += rs[j];
-    if (s_ == 1.2345e-30f) asm volatile("trap;");
-    *clk_mid = clock64();
-  }
-#endif
   // plane sums: the xor-butterfly 1,2,4 over the 8 lanes (rows) of a group, for six slots at once as a
   // reduce-scatter -- at every step a lane keeps half of its values and hands the other half to its
   // partner, so the six sums cost 3 + 2 + 1 shuffles instead of 18.  Every sum is still formed as
@@ -1226,7 +1218,7 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
   dense_pass<false>(sm, ag, l, -1, false, TdScalars{0.f, 0.f, 0.f, 0.f}, make_uint2(0, 0), make_uint2(0, 0));
   cta_barrier();  // B1
 #ifdef DCA_PHASE_CLOCK
-  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned ph[6] = {0, 0, 0, 0, 0, 0};
 #endif
 #pragma unroll 1
   for (long long it = 0; it < a.max_events; ++it) {
@@ -1239,19 +1231,14 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
     const VTree vt = q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r);
     dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
+    if (l.vw == 0 && lane_id() == 0) sm.v_pub = vt.val;
     DCA_CLK(c1);
     cta_barrier();  // B2
     DCA_CLKB(c2);
     const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
-#ifdef DCA_PHASE_CLOCK
-    long long cm;
-    dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r, &cm);
-    ph[6] += (unsigned long long)(cm - c3);
-#else
     dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
-#endif
     DCA_CLK(c4);
     if (sync_end) cta_barrier();
     cta_barrier();  // B1
@@ -1261,7 +1248,7 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
   }
 #ifdef DCA_PHASE_CLOCK
   if (lane_id() == 0)
-    for (int i = 0; i < 8; ++i) atomicAdd(&g_phase[l.vw][i], ph[i]);
+    for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[l.vw][i], (unsigned long long)ph[i]);
 #endif
   cta_barrier();
   stage_out(sm, g);
@@ -1287,7 +1274,7 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   cta_barrier();  // B1
   long long it = 0;
 #ifdef DCA_PHASE_CLOCK
-  unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned ph[6] = {0, 0, 0, 0, 0, 0};
 #endif
 #pragma unroll 1
   for (; it < a.max_events; ++it) {
@@ -1298,15 +1285,18 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const double time = ev.time;
     const bool is_end = type == EV_END;
     DCA_CLK(c0);
-    DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
-    const VTree vt = v_tree(sm);
-    dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
+    // (this warp needs V(s) only for the TD error it logs and tests: the agents publish it; the TD scalars
+    //  of the weight update are not needed here)
+    const DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
     ev_prepare(sm, e, ev);
     DCA_CLK(c1);
     // (ev_env_push / ev_env_pop do not depend on the chosen channel and could run before B2; measured on
     //  B200 that makes this warp the late one at B2: 245 / 233 M events/s instead of 251 M)
     cta_barrier();  // B2
     DCA_CLKB(c2);
+    VTree vt;
+    vt.val = sm.v_pub;
+    vt.dotg = 0.0f;
     const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
     const int pend_slot = ev_env_push(sm, e, type, cell, time, n > 0);       // Simulator.hs:101-128: new events
@@ -1359,7 +1349,7 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   }
 #ifdef DCA_PHASE_CLOCK
   if (lane == 0)
-    for (int i = 0; i < 8; ++i) atomicAdd(&g_phase[3][i], ph[i]);
+    for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[3][i], (unsigned long long)ph[i]);
 #endif
   cta_barrier();
   stage_out(sm, g);

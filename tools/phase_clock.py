@@ -21,7 +21,7 @@ with Replicas(Opt(n_replicas=n_rep, n_events=warm + n_ev, order="fast", rng="phi
     ms = s.run(n_ev)
     h.dca_debug_phase(out, 1)
     print(f"{n_rep} x {n_ev}: {ms:.2f} ms, {n_rep*n_ev/ms/1e3:.2f} M events/s")
-    names = ["eval", "wait B2", "decide", "update", "wait B1", "total", "slots"]
+    names = ["eval", "wait B2", "decide", "update", "wait B1", "total"]
     for role in range(4):
-        v = [out[role * 8 + i] / (n_rep * n_ev) for i in range(7)]
+        v = [out[role * 8 + i] / (n_rep * n_ev) for i in range(6)]
         print(("agent %d" % role if role < 3 else "event  "), "  ".join(f"{n} {x:7.0f}" for n, x in zip(names, v)))
