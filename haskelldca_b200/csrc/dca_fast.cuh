@@ -99,6 +99,10 @@ static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && o
               sizeof(Ev) % 8 == 0, "SmemF alignment");
 
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" ::: "memory"); }
+// named barrier 1, 96 threads (see agent_candidates): the event warp (next event published) and agent warp 2 (cnt2 moved to the
+// afterstate) arrive, agent warp 1 waits
+__device__ __forceinline__ void cand_signal() { asm volatile("bar.arrive 1, 96;" ::: "memory"); }
+__device__ __forceinline__ void cand_wait() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
 
 #ifdef DCA_PHASE_CLOCK  // development only: cycles per role (virtual warp) and phase, summed over CTAs and events
 __device__ unsigned long long g_phase[4][8];
@@ -302,7 +306,7 @@ __device__ __forceinline__ Lane make_lane() {
 //   g = fma(-cdot, x', fma(ctd, x, cavg));  w' = w - g;  wg' = fma(sg, x, wg)   (Agent.hs:67-76)
 // and the row sums of x'.w' -> plane sums P, x'.wg' -> warp sums Wg (for the next event).
 // Without UPDATE only the sums of the current state are formed.
-template <bool UPDATE>
+template <bool UPDATE, bool SIGNAL = false>
 __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, const int act, const bool is_end,
                                            const TdScalars td, const uint2 n4b_r, const uint2 n2b_r) {
   const int wid = l.vw;
@@ -323,6 +327,7 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
     *reinterpret_cast<uint2*>(&sm.cnt2[co]) = is_end ? bsub(cr, n2b_r) : badd(cr, n2b_r);
   }
+  if (UPDATE && SIGNAL && wid == 2) cand_signal();  // warp-uniform: cnt2 is in its afterstate
 #pragma unroll
   for (int j = 0; j < NSLOT; ++j) {
     const bool last = j == NSLOT - 1;
@@ -789,6 +794,45 @@ __device__ __forceinline__ void ev_candidates(const SmemF& sm, Ev& ev, const int
   __syncwarp();
 }
 
+// The run kernel splits that work.  The event warp is the longest dependency chain of the update phase
+// and the agent warps finish their dense pass well before it, so the event warp only publishes the next
+// event and the row masks of its cell (ev_masks) and signals named barrier 1; agent warp 1 waits there
+// after its dense pass and builds the candidate list (agent_candidates) -- by then cnt2 and the grid are
+// in their afterstate (agent warp 2 signals the same barrier after moving cnt2, the grid bit precedes the
+// event warp's signal), so no channel needs a special case.
+constexpr int CAND_WARP = 1;  // the agent warp that builds the candidate list
+__device__ __forceinline__ void ev_masks(Ev& ev, const int cell) {
+  const int lane = lane_id();
+  const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
+  if (lane < 8) {
+    ev.n4b[lane] = (lane < 7) ? spread7((uint32_t)(n4 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
+    ev.n2b[lane] = (lane < 7) ? spread7((uint32_t)(n2 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
+  }
+}
+__device__ __forceinline__ void agent_candidates(const SmemF& sm, Ev& ev) {
+  const int lane = lane_id();
+  const int cell = ev.cell;
+  uint32_t m[3];
+  if (ev.type == EV_END) {  // inuseChs, Gridfuncs.hs:86-87
+    const uint4 g = *reinterpret_cast<const uint4*>(&sm.grid[cell][0]);
+    m[0] = g.x; m[1] = g.y; m[2] = g.z;
+  } else {                  // eligibleChs, Gridfuncs.hs:69-82  <=>  nobody within distance 2 (incl. the cell) uses ch
+    const int pos = c_tab.pos[cell];
+    const uint8_t c0 = sm.cnt2[lane * PLANE + pos], c1 = sm.cnt2[(lane + 32) * PLANE + pos];
+    const uint8_t c2 = sm.cnt2[(lane < 6 ? lane + 64 : 0) * PLANE + pos];
+    m[0] = __ballot_sync(0xffffffffu, c0 == 0);
+    m[1] = __ballot_sync(0xffffffffu, c1 == 0);
+    m[2] = __ballot_sync(0xffffffffu, lane < 6 && c2 == 0);
+  }
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if ((m[j] >> lane) & 1u) ev.cand[base + __popc(m[j] & ((1u << lane) - 1u))] = (uint8_t)(32 * j + lane);
+    base += __popc(m[j]);
+  }
+  if (lane == 0) ev.ncand = base;
+}
+
 // ---- the event queue (EventGen, src/EventGen/Internal.hs:44-53) as a dense slot table with
 // per-block minima: pop = argmin over (time, id) (EventGen.hs:39-50) costs one 22-wide reduction
 // plus the re-scan of the one or two 32-slot blocks it touched.
@@ -1238,7 +1282,11 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
-    dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
+    dense_pass<true, true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
+    if (l.vw == CAND_WARP) {  // warp-uniform: the next event's candidate channels (getAction, Simulator.hs:161-165)
+      cand_wait();
+      agent_candidates(sm, sm.ev[(it & 1) ^ 1]);
+    }
     DCA_CLK(c4);
     if (sync_end) cta_barrier();
     cta_barrier();  // B1
@@ -1302,7 +1350,9 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const int pend_slot = ev_env_push(sm, e, type, cell, time, n > 0);       // Simulator.hs:101-128: new events
     const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
     ev_env_post(sm, nx, en, type, cell, ev_ch, d.act);                       // the channel-dependent rest
-    ev_candidates(sm, nx, d.act);
+    ev_masks(nx, en.cell);
+    __syncwarp();
+    cand_signal();  // next event, grid bit and masks are written: agent warp 1 builds the candidate list
     e.iter += 1;  // Simulator.hs:131
     // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
     int stop = ST_RUNNING;
