@@ -1054,6 +1054,7 @@ __device__ __forceinline__ EnvNext ev_env_pop(SmemF& sm, EvRegs& e, const int ty
 }
 
 // the channel-dependent rest, once `act` (-1 = Nothing) is known; writes the next event to `out`
+template <bool GRID_BIT = true>
 __device__ __forceinline__ void ev_env_post(SmemF& sm, Ev& out, EnvNext nx, const int type, const int cell,
                                             const int ev_ch, const int act) {
   const int lane = lane_id();
@@ -1066,7 +1067,7 @@ __device__ __forceinline__ void ev_env_post(SmemF& sm, Ev& out, EnvNext nx, cons
     else rekey = true;
   }
   if (lane == 0) {
-    if (act >= 0) sm.grid[cell][act >> 5] ^= 1u << (act & 31);  // executeAction, Gridfuncs.hs:105-110
+    if (GRID_BIT && act >= 0) sm.grid[cell][act >> 5] ^= 1u << (act & 31);  // executeAction, Gridfuncs.hs:105-110
     if (nx.pend_slot >= 0) {
       sm.q_key[nx.pend_slot] = (uint16_t)((cell << 7) | act);
       sm.end_slot[cell][act] = (uint16_t)nx.pend_slot;
@@ -1347,12 +1348,15 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     vt.dotg = 0.0f;
     const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
+    if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);  // executeAction, Gridfuncs.hs:105-110
     const int pend_slot = ev_env_push(sm, e, type, cell, time, n > 0);       // Simulator.hs:101-128: new events
     const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
-    ev_env_post(sm, nx, en, type, cell, ev_ch, d.act);                       // the channel-dependent rest
+    // the candidate list of the next event needs its kind and cell, the grid and cnt2: all known here
+    if (lane == 0) { nx.type = en.type; nx.cell = en.cell; }
     ev_masks(nx, en.cell);
     __syncwarp();
-    cand_signal();  // next event, grid bit and masks are written: agent warp 1 builds the candidate list
+    cand_signal();  // agent warp 1 builds the candidate list
+    ev_env_post<false>(sm, nx, en, type, cell, ev_ch, d.act);                // the channel-dependent rest
     e.iter += 1;  // Simulator.hs:131
     // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
     int stop = ST_RUNNING;
