@@ -9,21 +9,24 @@
 //              DCA_WG_REGS), wNet in shared memory (the afterstate evaluation needs it
 //              with a flexible lane mapping).  96 registers, 43.6 KB -> 5 CTAs per SM.
 //   warp 3     "event" warp: event queue, random numbers, statistics, grid bits,
-//              candidate channels, stop rules (environmentStep, src/Simulator.hs:101-134).
+//              stop rules (environmentStep, src/Simulator.hs:101-134).  It is the longest
+//              dependency chain of an event, so agent warp 1 builds the next event's
+//              candidate channels for it once its own dense pass is done.
 //
 // Per event (runStep, src/SimRunner.hs:60-97) -- two CTA barriers:
 //   B1 -> agents: V(s) = x.w from the plane sums (butterfly), then every candidate
 //         channel on its own 8-lane group: the two planes the action touches are
 //         re-evaluated and substituted into the V tree (selectAction,
 //         src/Simulator.hs:185-205 with incAfterStateFreps, src/Gridfuncs.hs:186-252).
-//         event warp: V(s), queue pre-scan, random draws.
+//         event warp: queue pre-scan, random draws (V(s) is published by the agents).
 //   B2 -> every thread: argmax (last maximum wins, src/AccUtils.hs:203-208) and the
 //         TD scalars (src/Agent.hs:62-78), replicated.
 //         agents: dense w / wGradCorr update (src/Agent.hs:67-76) fused with moving
 //         frep / cnt2 to the chosen afterstate (the owners of the touched rows do it)
 //         and with the next event's row sums.
 //         event warp, concurrently: grid bit (src/Gridfuncs.hs:105-110), statistics,
-//         new events, the next event and its candidate channels, stop rules.
+//         new events, the next event (published to agent warp 1 through named barrier 1,
+//         which then builds its candidate channels), stop rules.
 //   -> B1
 //
 // The fp32 arithmetic is the FAST order specified in DESIGN.md ("Arithmetic
