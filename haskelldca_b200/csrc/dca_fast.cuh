@@ -814,13 +814,14 @@ __device__ __forceinline__ void ev_masks(Ev& ev, const int cell) {
 }
 __device__ __forceinline__ void agent_candidates(const SmemF& sm, Ev& ev) {
   const int lane = lane_id();
-  const int cell = ev.cell;
+  const int2 tc = *reinterpret_cast<const int2*>(&ev.type);  // (type, cell): adjacent, 8-byte aligned -- one load
+  const int cell = tc.y;
   uint32_t m[3];
-  if (ev.type == EV_END) {  // inuseChs, Gridfuncs.hs:86-87
+  if (tc.x == EV_END) {     // inuseChs, Gridfuncs.hs:86-87
     const uint4 g = *reinterpret_cast<const uint4*>(&sm.grid[cell][0]);
     m[0] = g.x; m[1] = g.y; m[2] = g.z;
   } else {                  // eligibleChs, Gridfuncs.hs:69-82  <=>  nobody within distance 2 (incl. the cell) uses ch
-    const int pos = c_tab.pos[cell];
+    const int pos = cell + (cell * 37 >> 8);  // (cell / 7) * 8 + cell % 7 for cell < 49
     const uint8_t c0 = sm.cnt2[lane * PLANE + pos], c1 = sm.cnt2[(lane + 32) * PLANE + pos];
     const uint8_t c2 = sm.cnt2[(lane < 6 ? lane + 64 : 0) * PLANE + pos];
     m[0] = __ballot_sync(0xffffffffu, c0 == 0);
