@@ -286,7 +286,7 @@ def main():
                          "kernel": "dca::fast::k_run_fast<false>", "peak_source": peak_src, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": n_rep * n_ev * ALG_BYTES_PER_EVENT,
                          "note": "achieved = events/s/GPU x 55 664 algorithmic bytes (r+w of wNet, wGradCorr per event, Agent.hs:67-76) over the "
-                                 "kernel's own CUDA-event duration; the kernel keeps a replica's weights on chip (shared memory + registers) for "
+                                 "kernel's own CUDA-event duration; the kernel keeps a replica's weights on chip (shared memory + tensor memory) for "
                                  "the whole launch, so DRAM traffic is one state blob in and out per replica per launch and frac > 1 is "
                                  "legitimate multi-event residency -- the binding limits are issue slots and the per-event dependency chain "
                                  "(profiles/: smsp__issue_active, stall reasons)"},
