@@ -447,11 +447,13 @@ int dca_run(dca_handle* h, int64_t max_events) {
   a.trace = h->d_trace;
   a.trace_cap = h->cfg.trace_capacity;
   const bool trace = h->d_trace != nullptr;
+  // (the TRACE instantiation of the fused FAST kernel also serves the verify flags: it has the extra per-event barrier)
+  const bool trace_fast = trace || a.verify_rc || a.verify_nb;
   const dim3 grid(h->n), block(128);
   const size_t smem = sizeof(Smem);
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->cfg.order == DCA_ORDER_FAST) {
-    if (trace) fast::k_run_fast<true><<<grid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
+    if (trace_fast) fast::k_run_fast<true><<<grid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
     else fast::k_run_fast<false><<<grid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
   } else {
     if (trace) k_run<ORDER_REF, true><<<grid, block, smem, h->stream>>>(a);

@@ -1251,12 +1251,12 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
 // The fused run kernel (dca_run, FAST order).  grid = n_replicas CTAs of 128.
 // The agent warps and the event warp run their own copies of the event loop
 // (separate register allocations) and meet at the CTA barriers.
-// sync_end (parity traces, verify flags): one more barrier per event so that the
+// sync_end (TRACE instantiation: parity traces, verify flags): one more barrier per event so that the
 // event warp sees the afterstate before it hashes / verifies it.
 // ---------------------------------------------------------------------------
 template <bool TRACE>
 __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState* g, Agent& ag) {
-  const bool sync_end = TRACE || a.verify_rc || a.verify_nb;
+  constexpr bool sync_end = TRACE;  // (the host launches the TRACE instantiation whenever a verify flag is set)
   const Lane l = make_lane();
   const int rc = l.rv ? l.r : 6;
   stage_in(sm, g);
@@ -1314,7 +1314,7 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
 
 template <bool TRACE>
 __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState* g, int rep) {
-  const bool sync_end = TRACE || a.verify_rc || a.verify_nb;
+  constexpr bool sync_end = TRACE;  // (the host launches the TRACE instantiation whenever a verify flag is set)
   const int lane = lane_id();
   stage_in(sm, g);
   float avgR = g->avg_reward;
