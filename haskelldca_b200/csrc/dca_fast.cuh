@@ -263,7 +263,6 @@ struct TdScalars {
 struct Lane {
   int vw;             // virtual warp (role) of this thread: 0..2 agent, 3 event
   int g8, r;          // lane group (0..11), row (0..7; 7 idles)
-  int xoff;           // byte offset of this lane's row in sm.x for slot 0 (+672 per slot)
   int woff;           // float offset of this lane's row in a half of sm.w for slot 0 (+336 per slot)
   bool rv;            // row valid
   int pidx;           // index in sm.P of the plane sum this lane ends up with in dense_pass (-1: none)
@@ -292,7 +291,6 @@ __device__ __forceinline__ Lane make_lane() {
   l.r = vt & 7;
   l.rv = l.r < 7;
   const int rc = l.rv ? l.r : 6;
-  l.xoff = l.g8 * PLANE + rc * ROWPAD;
   l.woff = (l.g8 * 7 + rc) * 4;
   {  // see the reduce-scatter in dense_pass: row 0 -> slot 0, 1 -> 3, 2 -> 2, 3 -> 5, 4 -> 1, 5 -> 4 (rows 6, 7 repeat 2, 3)
     const bool b0 = l.r & 1, b1 = l.r & 2, b2 = l.r & 4;
@@ -338,8 +336,8 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     const bool pv = last ? l.g8 != SLOTP - 1 : true;
     const int f = SLOTP * j + l.g8 - (pv ? 0 : 1);
     const bool valid = pv && l.rv;
-    const int xo_ = l.xoff + j * SLOTP * PLANE - (pv ? 0 : PLANE);
     const int wo_ = l.woff + j * SLOTP * 28 - (pv ? 0 : 28);
+    const int xo_ = 2 * wo_;  // byte offset of the same row in sm.x: 56 f + 8 r = 2 (28 f + 4 r)
     const uint2 xb = *reinterpret_cast<const uint2*>(&sm.x[xo_]);
     const float4 wa = *reinterpret_cast<const float4*>(&sm.w[0][wo_]);
     const float4 wb = *reinterpret_cast<const float4*>(&sm.w[1][wo_]);
