@@ -801,7 +801,10 @@ __device__ __forceinline__ void ev_candidates(const SmemF& sm, Ev& ev, const int
 // after its dense pass and builds the candidate list (agent_candidates) -- by then cnt2 and the grid are
 // in their afterstate (agent warp 2 signals the same barrier after moving cnt2, the grid bit precedes the
 // event warp's signal), so no channel needs a special case.
-constexpr int CAND_WARP = 1;  // the agent warp that builds the candidate list
+#ifndef DCA_CAND_WARP
+#define DCA_CAND_WARP 1
+#endif
+constexpr int CAND_WARP = DCA_CAND_WARP;  // the agent warp that builds the candidate list
 __device__ __forceinline__ void ev_masks(Ev& ev, const int cell) {
   const int lane = lane_id();
   const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
