@@ -222,6 +222,8 @@ __device__ __forceinline__ void wg_put(Agent& ag, const int j, const WgRow& g) {
 }
 __device__ __forceinline__ void wg_commit() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 constexpr uint32_t TMEM_COLS = 64;
+static_assert(8 * NSLOT <= TMEM_COLS, "six rows of eight columns per lane");
+static_assert(DCA_MIN_CTAS * TMEM_COLS <= 512, "an SM has 512 tensor-memory columns: every resident CTA must get its share");
 // CTA-wide: hardware warp 0 allocates, everybody learns the base
 __device__ __forceinline__ void tmem_open(SmemF& sm, Agent& ag) {
   if ((threadIdx.x >> 5) == 0) {
