@@ -117,6 +117,40 @@ def cpu_leg(order, n_replicas, n_events, threads):
     return total / dt, dt, total, stats
 
 
+def oracle_spot_check(sims, first, n_rep, n_ev, hoff_prob):
+    """After the timed region: the replicas this rank just ran (k_run_fast<false>, the benchmarked instantiation)
+    against their own oracle runs, bit for bit -- one replica of every wave / event-warp rotation of the launch
+    (block ids 0, 740, 1480, 2220 on a 148-SM B200) and the last one.  The oracle runs proceed on host threads
+    (ctypes releases the GIL).  Returns (ok, replicas checked, first mismatch or None)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+    import pyoracle as po
+
+    spot = sorted({r for r in (0, 740, 1480, 2220, n_rep - 1) if 0 <= r < n_rep})
+
+    def one(r):
+        o = po.Sim(po.default_opt(order=po.ORDER_FAST, rng_mode=po.RNG_PHILOX, seed=0, replica=first + r, n_events=n_ev,
+                                  hoff_prob=hoff_prob))
+        o.run(n_ev)
+        return o.read()
+
+    with ThreadPoolExecutor(max_workers=len(spot)) as ex:
+        wants = list(ex.map(one, spot))
+    u32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    for r, want in zip(spot, wants):
+        got = sims.read_state(r)
+        for k in ("grid", "frep", "stats"):
+            if not np.array_equal(got[k], want[k]):
+                return False, [first + x for x in spot], f"replica {first + r}: {k}"
+        for k in ("w", "wg", "avg_reward"):
+            if not np.array_equal(u32(got[k]), u32(want[k])):
+                return False, [first + x for x in spot], f"replica {first + r}: {k}"
+        if got["iter"] != want["iter"] or got["event"] != want["event"]:
+            return False, [first + x for x in spot], f"replica {first + r}: iter / next event"
+    return True, [first + x for x in spot], None
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's algorithm on the host cores.  haskelldca is Haskell/Accelerate
     (no GHC, no LLVM 6 here), so this arm runs the oracle port in the reference's own arithmetic
@@ -162,6 +196,7 @@ def main():
     ap.add_argument("--cpu-events", type=int, default=100000, dest="cpu_events")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-spot-check", action="store_true", help="skip the oracle spot check of the timed configuration")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -267,6 +302,22 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": events_all * args.steps / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
 
+    # the timed configuration against the oracle (every rank checks replicas of its own shard; the state on the
+    # device is the one the last step left behind)
+    spot = None
+    if not args.no_spot_check:
+        ok_spot, spot_reps, spot_msg = oracle_spot_check(sims, first, n_rep, n_ev, args.hoff_prob)
+        tk = torch.tensor([1 if ok_spot else 0, len(spot_reps)], dtype=torch.int64, device="cuda")
+        if world > 1:
+            tmin = tk[:1].clone()
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+            tsum = tk[1:].clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            tk = torch.cat([tmin, tsum])
+        spot = {"ok": bool(tk[0].item()), "replicas_checked_all_ranks": int(tk[1].item()), "rank0_replicas": spot_reps,
+                "rank0_mismatch": spot_msg, "events": n_ev,
+                "what": "grid, frep, stats, wNet, wGradCorr, avgReward, iter, next event bit-exact vs the CPU oracle (FAST order)"}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         traffic, traffic_src = measured_traffic()
@@ -294,7 +345,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "checks": {"all_replicas_success": bool(ok_local), "blocking_probability": bp, "events_per_step": events_all,
-                       "wall_ms_per_step": wall_ms_max / args.steps},
+                       "wall_ms_per_step": wall_ms_max / args.steps,
+                       "oracle_spot_check": spot["ok"] if spot else None, "oracle_spot_check_detail": spot},
         }
         if not args.no_cpu_baseline and world == 1:
             import pyoracle as po

@@ -17,7 +17,7 @@ GRID_SIZE, FREP_SIZE = 3430, 3479
 ORDER_REF, ORDER_FAST = 0, 1
 RNG_TAPE, RNG_PHILOX = 0, 1
 NEW, END, HOFF = 0, 1, 2
-RUNNING, SUCCESS, ZERO_LOSS, NAN_LOSS, REUSE_VIOLATED, NELIG_OVERFLOW, TAPE_EXHAUSTED = range(7)
+RUNNING, SUCCESS, ZERO_LOSS, NAN_LOSS, REUSE_VIOLATED, NELIG_OVERFLOW, TAPE_EXHAUSTED, UNINITIALIZED, QUEUE_OVERFLOW = range(9)
 
 
 class Config(C.Structure):

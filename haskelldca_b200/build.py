@@ -10,7 +10,10 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libdca_b200.so")
 SOURCES = ["dca_b200.cu"]
-DEPS = ["dca_b200.cu", "dca_kernels.cuh", "dca_fast.cuh", "dca_state.h", os.path.join("..", "..", "include", "dca_b200.h")]
+def deps():
+    """every source the library is built from: all of csrc/ plus the C-ABI header"""
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [
+        os.path.join(os.path.dirname(HERE), "include", "dca_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -31,7 +34,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in deps())
 
 
 def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str | None = None) -> str:

@@ -107,6 +107,49 @@ bool g_tab_uploaded[64] = {false};
 
 }  // namespace
 
+namespace {
+struct OpIO {  // host-visible part; the same layout on the device and in pinned host memory
+  // inputs, ordered so that every operator's inputs are one contiguous range starting at `grid`
+  uint8_t grid[3456];            // DCA_GRID_SIZE rounded up to 64
+  float w[FREP + 1];
+  float wg[FREP + 1];
+  long long frep[FREP + 1];
+  long long nfrep[FREP + 1];
+  long long chs[NCH + 2];
+  // outputs
+  long long out_frep[FREP + 1];
+  long long reward;
+  ops::BackwardOut bout;
+  int n, ch, violates;
+  float dot;
+};
+static_assert(DCA_GRID_SIZE <= 3456, "grid staging");
+
+struct OpScratch {
+  bool ready = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  OpIO* d_io = nullptr;       // device
+  OpIO* h_io = nullptr;       // pinned host mirror
+  RepState* st = nullptr;     // a scratch replica blob (grid masks, cnt2, frep of the caller's grid)
+  long long* afreps = nullptr;  // [NCH][FREP]
+  float* q = nullptr;         // [72]
+  std::mutex mu;
+  void release() {
+    if (d_io) cudaFree(d_io);
+    if (h_io) cudaFreeHost(h_io);
+    if (st) cudaFree(st);
+    if (afreps) cudaFree(afreps);
+    if (q) cudaFree(q);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+    d_io = h_io = nullptr; st = nullptr; afreps = nullptr; q = nullptr; stream = nullptr;
+    ready = false;
+  }
+};
+
+}  // namespace
+
 struct dca_handle {
   dca_config cfg{};
   int device = 0;
@@ -135,6 +178,7 @@ struct dca_handle {
   float last_ms = 0.f;
   long long launches = 0;
   int warps = 4;
+  OpScratch scratch;  // staging of dca_write_state (device + pinned host), allocated at first use
 };
 
 namespace {
@@ -144,6 +188,9 @@ int fail(dca_handle* h, int code, const char* msg) {
   if (h) h->err = msg;
   return code;
 }
+
+int scratch_alloc(dca_handle* h, OpScratch& s, int device, cudaStream_t stream);
+int scratch_reserve(dca_handle* h) { return scratch_alloc(h, h->scratch, h->device, h->stream); }
 
 int upload_tables(dca_handle* h, int device) {
   std::lock_guard<std::mutex> lk(g_tab_mutex);
@@ -270,6 +317,7 @@ int dca_destroy(dca_handle* h) {
   if (!h) return DCA_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  h->scratch.release();
   cudaFree(h->d_states);
   cudaFree(h->d_mean_new); cudaFree(h->d_call_dur); cudaFree(h->d_call_dur_hoff); cudaFree(h->d_hoff_prob);
   cudaFree(h->d_a_net); cudaFree(h->d_a_avg); cudaFree(h->d_a_grad);
@@ -430,6 +478,13 @@ int dca_set_rng_mt19937(dca_handle* h, int32_t replica, uint64_t seed, size_t n_
 int dca_run(dca_handle* h, int64_t max_events) {
   if (!h || max_events < 0) return fail(h, DCA_ERR_ARG, "dca_run: bad argument");
   CK(cudaSetDevice(h->device));
+  if (h->cfg.rng_mode == DCA_RNG_TAPE)  // a replica without its 49 initial draws was never initialised (DCA_UNINITIALIZED)
+    for (int i = 0; i < h->n; ++i)
+      if (h->tape_w[i].size() < (size_t)NCELL) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "dca_run: replica %d has no random tape (dca_set_rng_tape / dca_set_rng_mt19937 with >= 49 draws first)", i);
+        return fail(h, DCA_ERR_STATE, buf);
+      }
   int rc = sync_tapes(h);
   if (rc) return rc;
   RunArgs a{};
@@ -493,6 +548,9 @@ static int step_launch(dca_handle* h, int replica, int mode, int r, int c, int i
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(host_out, h->d_stepout, sizeof(StepOut), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (host_out->ch == STEP_BAD_CHANNEL)
+    return fail(h, DCA_ERR_ARG, is_end ? "dca_grid_step_train: the channel is not in use at this cell (nothing was changed)"
+                                       : "dca_grid_step_train: the channel is not eligible at this cell (nothing was changed)");
   return DCA_OK;
 }
 
@@ -562,25 +620,25 @@ int dca_write_state(dca_handle* h, int32_t replica, const uint8_t* grid, const f
   if (bad_replica(h, replica)) return fail(h, DCA_ERR_ARG, "dca_write_state: bad replica");
   CK(cudaSetDevice(h->device));
   RepState* st = h->d_states + replica;
+  int rc = scratch_reserve(h);
+  if (rc) return rc;
+  OpScratch& sc = h->scratch;
+  OpIO *hi = sc.h_io, *di = sc.d_io;
+  if (grid) memcpy(hi->grid, grid, DCA_GRID_SIZE);
+  if (wnet) memcpy(hi->w, wnet, FREP * 4);
+  if (wgrad) memcpy(hi->wg, wgrad, FREP * 4);
+  CK(cudaMemcpyAsync(di, hi, offsetof(OpIO, frep), cudaMemcpyHostToDevice, h->stream));  // grid, w, wg in one copy
   if (grid) {
-    uint8_t* d_grid = nullptr;
-    CK(cudaMalloc(&d_grid, DCA_GRID_SIZE));
-    CK(cudaMemcpyAsync(d_grid, grid, DCA_GRID_SIZE, cudaMemcpyHostToDevice, h->stream));
-    k_gf_load_grid<<<1, 256, 0, h->stream>>>(st, d_grid);
+    k_gf_load_grid<<<1, 256, 0, h->stream>>>(st, di->grid);
     h->launches++;
-    CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_grid);
+    CK(cudaGetLastError());
   }
   if (wnet || wgrad) {
-    float *dw = nullptr, *dg = nullptr;
-    if (wnet) { CK(cudaMalloc(&dw, FREP * 4)); CK(cudaMemcpyAsync(dw, wnet, FREP * 4, cudaMemcpyHostToDevice, h->stream)); }
-    if (wgrad) { CK(cudaMalloc(&dg, FREP * 4)); CK(cudaMemcpyAsync(dg, wgrad, FREP * 4, cudaMemcpyHostToDevice, h->stream)); }
-    k_pack_weights<<<1, 256, 0, h->stream>>>(st, dw, dg);
+    k_pack_weights<<<1, 256, 0, h->stream>>>(st, wnet ? di->w : nullptr, wgrad ? di->wg : nullptr);
     h->launches++;
-    CK(cudaStreamSynchronize(h->stream));
-    cudaFree(dw);
-    cudaFree(dg);
+    CK(cudaGetLastError());
   }
+  CK(cudaStreamSynchronize(h->stream));
   if (avg_reward)
     CK(cudaMemcpy(reinterpret_cast<unsigned char*>(st) + offsetof(RepState, avg_reward), avg_reward, 4, cudaMemcpyHostToDevice));
   CK(cudaGetLastError());
@@ -590,13 +648,31 @@ int dca_write_state(dca_handle* h, int32_t replica, const uint8_t* grid, const f
 // ---- checkpoint / resume: the replica blobs verbatim behind a small header ----------
 namespace {
 struct CkptHeader {
-  uint64_t magic;      // "DCAB200\1"
+  uint64_t magic;      // "DCAB200\2"
+  uint32_t version;    // layout version of this header + RepState
   uint32_t blob_bytes; // sizeof(RepState)
   int32_t n_replicas;
   int32_t order, rng_mode;
-  uint64_t reserved;
+  int32_t pad;
+  uint64_t seed;          // Philox key (the stream continues only under the same key) ...
+  uint64_t first_replica; // ... and the same stream ids
+  uint64_t tape_hash;     // DCA_RNG_TAPE: hash over every replica's tape length and words (0 in Philox mode)
 };
-constexpr uint64_t kCkptMagic = 0x0130303242414344ULL;
+constexpr uint64_t kCkptMagic = 0x0230303242414344ULL;
+constexpr uint32_t kCkptVersion = 2;
+
+uint64_t tape_hash(const dca_handle* h) {
+  if (h->cfg.rng_mode != DCA_RNG_TAPE) return 0;
+  uint64_t x = 0xCBF29CE484222325ULL;  // FNV-1a over (length, words) of every replica
+  auto mixin = [&](uint64_t v) {
+    for (int b = 0; b < 8; ++b) { x ^= (v >> (8 * b)) & 0xFF; x *= 0x100000001B3ULL; }
+  };
+  for (int i = 0; i < h->n; ++i) {
+    mixin(h->tape_w[i].size());
+    for (unsigned long long w : h->tape_w[i]) mixin(w);
+  }
+  return x ? x : 1;
+}
 }  // namespace
 
 size_t dca_checkpoint_size(const dca_handle* h) {
@@ -606,7 +682,8 @@ size_t dca_checkpoint_size(const dca_handle* h) {
 int dca_checkpoint_save(dca_handle* h, void* buf, size_t size) {
   if (!h || !buf || size < dca_checkpoint_size(h)) return fail(h, DCA_ERR_ARG, "dca_checkpoint_save: bad argument");
   CK(cudaSetDevice(h->device));
-  CkptHeader hd{kCkptMagic, (uint32_t)sizeof(RepState), h->n, h->cfg.order, h->cfg.rng_mode, 0};
+  CkptHeader hd{kCkptMagic, kCkptVersion, (uint32_t)sizeof(RepState), h->n, h->cfg.order, h->cfg.rng_mode, 0,
+                h->cfg.seed, h->cfg.first_replica, tape_hash(h)};
   memcpy(buf, &hd, sizeof hd);
   CK(cudaMemcpyAsync(static_cast<char*>(buf) + sizeof hd, h->d_states, sizeof(RepState) * (size_t)h->n,
                      cudaMemcpyDeviceToHost, h->stream));
@@ -618,9 +695,15 @@ int dca_checkpoint_load(dca_handle* h, const void* buf, size_t size) {
   if (!h || !buf || size < dca_checkpoint_size(h)) return fail(h, DCA_ERR_ARG, "dca_checkpoint_load: bad argument");
   CkptHeader hd;
   memcpy(&hd, buf, sizeof hd);
-  if (hd.magic != kCkptMagic || hd.blob_bytes != sizeof(RepState) || hd.n_replicas != h->n ||
+  if (hd.magic != kCkptMagic || hd.version != kCkptVersion || hd.blob_bytes != sizeof(RepState) || hd.n_replicas != h->n ||
       hd.order != h->cfg.order || hd.rng_mode != h->cfg.rng_mode)
-    return fail(h, DCA_ERR_STATE, "dca_checkpoint_load: the blob does not match this handle (replicas, order, rng mode or layout)");
+    return fail(h, DCA_ERR_STATE, "dca_checkpoint_load: the blob does not match this handle (replicas, order, rng mode or layout version)");
+  // the random stream lives in the handle (Philox key and stream ids, or the tapes), not in the blob: continuing
+  // "bit for bit" needs the same one
+  if (hd.seed != h->cfg.seed || hd.first_replica != h->cfg.first_replica)
+    return fail(h, DCA_ERR_STATE, "dca_checkpoint_load: the blob was saved under a different seed / first_replica");
+  if (hd.tape_hash != tape_hash(h))
+    return fail(h, DCA_ERR_STATE, "dca_checkpoint_load: the blob was saved with different random tapes");
   CK(cudaSetDevice(h->device));
   int rc = sync_tapes(h);
   if (rc) return rc;
@@ -753,50 +836,94 @@ int dca_get_neighs(int32_t d, int32_t r, int32_t c, int32_t include_self, int32_
   return DCA_OK;
 }
 
+}  // extern "C"
+
+// The pure operators work on caller-owned HOST arrays.  Each device keeps ONE scratch for them, allocated at the
+// first call and reused: a device block, a pinned host mirror of its host-visible part, and a stream.  A call
+// copies its inputs into the pinned mirror, issues one H2D copy, its kernels and one D2H copy on that stream and
+// synchronises once -- no cudaMalloc / cudaFree and no mid-pipeline round trip per call (the candidate count of
+// getAction stays on the device).
 namespace {
-struct GfScratch {  // a scratch replica blob + staging buffers on `device`
-  RepState* st = nullptr;
-  uint8_t* grid = nullptr;
-  long long* frep = nullptr;
-  long long* chs = nullptr;
-  int* n = nullptr;
-  ~GfScratch() { cudaFree(st); cudaFree(grid); cudaFree(frep); cudaFree(chs); cudaFree(n); }
-};
-int gf_begin(int device, const uint8_t* grid, GfScratch& g) {
-  dca_handle* h = nullptr;
-  if (!grid) return fail(h, DCA_ERR_ARG, "gridfuncs: null grid");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(h, DCA_ERR_NO_DEVICE, "gridfuncs: no CUDA device (there is no CPU fallback)");
-  int rc = set_device(h, device);
-  if (rc) return rc;
-  CK(cudaMalloc(&g.st, sizeof(RepState)));
-  CK(cudaMalloc(&g.grid, DCA_GRID_SIZE));
-  CK(cudaMalloc(&g.frep, sizeof(long long) * FREP));
-  CK(cudaMalloc(&g.chs, sizeof(long long) * NCH));
-  CK(cudaMalloc(&g.n, sizeof(int)));
-  CK(cudaMemcpy(g.grid, grid, DCA_GRID_SIZE, cudaMemcpyHostToDevice));
-  k_gf_load_grid<<<1, 256>>>(g.st, g.grid);
-  CK(cudaGetLastError());
+
+OpScratch g_dev_scratch[64];
+
+int scratch_alloc(dca_handle* h, OpScratch& s, int device, cudaStream_t stream) {
+  if (s.ready) return DCA_OK;
+  s.device = device;
+  if (stream) { s.stream = stream; s.own_stream = false; }
+  else { CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)); s.own_stream = true; }
+  CK(cudaMalloc(&s.d_io, sizeof(OpIO)));
+  CK(cudaMallocHost(&s.h_io, sizeof(OpIO)));
+  CK(cudaMalloc(&s.st, sizeof(RepState)));
+  CK(cudaMalloc(&s.afreps, sizeof(long long) * (size_t)NCH * FREP));
+  CK(cudaMalloc(&s.q, sizeof(float) * 72));
+  CK(cudaMemsetAsync(s.d_io, 0, sizeof(OpIO), s.stream));
+  memset(s.h_io, 0, sizeof(OpIO));
+  s.ready = true;
   return DCA_OK;
 }
+
+// the per-device scratch of the stateless operators (caller holds s.mu)
+int dev_scratch(int device, OpScratch** out) {
+  dca_handle* h = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, DCA_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev || device >= 64) return fail(h, DCA_ERR_ARG, "bad device ordinal");
+  int rc = set_device(h, device);
+  if (rc) return rc;
+  OpScratch& s = g_dev_scratch[device];
+  rc = scratch_alloc(h, s, device, nullptr);
+  if (rc) { s.release(); return rc; }
+  *out = &s;
+  return DCA_OK;
+}
+
+#define IO_OFF(field) offsetof(OpIO, field)
+// host -> device / device -> host of the byte range [from, to) of the OpIO block
+int io_h2d(OpScratch& s, size_t from, size_t to) {
+  dca_handle* h = nullptr;
+  CK(cudaMemcpyAsync(reinterpret_cast<char*>(s.d_io) + from, reinterpret_cast<char*>(s.h_io) + from, to - from,
+                     cudaMemcpyHostToDevice, s.stream));
+  return DCA_OK;
+}
+int io_d2h(OpScratch& s, size_t from, size_t to) {
+  dca_handle* h = nullptr;
+  CK(cudaMemcpyAsync(reinterpret_cast<char*>(s.h_io) + from, reinterpret_cast<char*>(s.d_io) + from, to - from,
+                     cudaMemcpyDeviceToHost, s.stream));
+  return DCA_OK;
+}
+int io_sync(OpScratch& s) {
+  dca_handle* h = nullptr;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s.stream));
+  return DCA_OK;
+}
+
+// grid bytes -> masks, cnt2, frep in the scratch blob (the caller's grid is already in h_io->grid)
+void launch_load_grid(OpScratch& s) { k_gf_load_grid<<<1, 256, 0, s.stream>>>(s.st, s.d_io->grid); }
+
 int gf_chs(int device, const uint8_t* grid, int r, int c, int is_end, int64_t* chs, int32_t* n) {
   dca_handle* h = nullptr;
-  if (r < 0 || r >= ROWS || c < 0 || c >= COLS || !chs || !n) return fail(h, DCA_ERR_ARG, "gridfuncs: bad argument");
-  GfScratch g;
-  int rc = gf_begin(device, grid, g);
+  if (!grid || r < 0 || r >= ROWS || c < 0 || c >= COLS || !chs || !n) return fail(h, DCA_ERR_ARG, "gridfuncs: bad argument");
+  OpScratch* sp = nullptr;
+  int rc = dev_scratch(device, &sp);
   if (rc) return rc;
-  k_gf_chs<<<1, 32>>>(g.st, r * COLS + c, is_end, g.chs, g.n);
-  CK(cudaGetLastError());
-  int cnt = 0;
-  CK(cudaMemcpy(&cnt, g.n, sizeof(int), cudaMemcpyDeviceToHost));
-  long long tmp[NCH];
-  CK(cudaMemcpy(tmp, g.chs, sizeof(long long) * NCH, cudaMemcpyDeviceToHost));
-  for (int i = 0; i < cnt; ++i) chs[i] = tmp[i];
+  OpScratch& s = *sp;
+  std::lock_guard<std::mutex> lk(s.mu);
+  memcpy(s.h_io->grid, grid, DCA_GRID_SIZE);
+  if ((rc = io_h2d(s, IO_OFF(grid), IO_OFF(w)))) return rc;
+  launch_load_grid(s);
+  k_gf_chs<<<1, 32, 0, s.stream>>>(s.st, r * COLS + c, is_end, s.d_io->chs, &s.d_io->n);
+  if ((rc = io_d2h(s, IO_OFF(chs), IO_OFF(out_frep))) || (rc = io_d2h(s, IO_OFF(n), IO_OFF(ch))) || (rc = io_sync(s))) return rc;
+  const int cnt = s.h_io->n;
+  for (int i = 0; i < cnt; ++i) chs[i] = s.h_io->chs[i];
   *n = cnt;
   return DCA_OK;
 }
 }  // namespace
+
+extern "C" {
 
 int dca_gf_eligible_chs(int32_t device, const uint8_t* grid, int32_t r, int32_t c, int64_t* chs, int32_t* n) {
   return gf_chs(device, grid, r, c, 0, chs, n);
@@ -807,110 +934,95 @@ int dca_gf_inuse_chs(int32_t device, const uint8_t* grid, int32_t r, int32_t c, 
 
 int dca_gf_feature_rep(int32_t device, const uint8_t* grid, int64_t* frep) {
   dca_handle* h = nullptr;
-  if (!frep) return fail(h, DCA_ERR_ARG, "dca_gf_feature_rep: null output");
-  GfScratch g;
-  int rc = gf_begin(device, grid, g);
+  if (!grid || !frep) return fail(h, DCA_ERR_ARG, "dca_gf_feature_rep: null argument");
+  OpScratch* sp = nullptr;
+  int rc = dev_scratch(device, &sp);
   if (rc) return rc;
-  k_gf_store_frep<<<1, 256>>>(g.st, g.frep);
-  CK(cudaGetLastError());
+  OpScratch& s = *sp;
+  std::lock_guard<std::mutex> lk(s.mu);
+  memcpy(s.h_io->grid, grid, DCA_GRID_SIZE);
+  if ((rc = io_h2d(s, IO_OFF(grid), IO_OFF(w)))) return rc;
+  launch_load_grid(s);
+  k_gf_store_frep<<<1, 256, 0, s.stream>>>(s.st, s.d_io->out_frep);
+  if ((rc = io_d2h(s, IO_OFF(out_frep), IO_OFF(reward))) || (rc = io_sync(s))) return rc;
   static_assert(sizeof(long long) == sizeof(int64_t), "int64");
-  CK(cudaMemcpy(frep, g.frep, sizeof(long long) * FREP, cudaMemcpyDeviceToHost));
+  memcpy(frep, s.h_io->out_frep, sizeof(int64_t) * FREP);
   return DCA_OK;
 }
 
 int dca_gf_inc_afterstate_freps(int32_t device, int32_t r, int32_t c, int32_t is_end, const int64_t* chs,
                                 int32_t n, const uint8_t* grid, const int64_t* frep, int64_t* out) {
   dca_handle* h = nullptr;
-  if (r < 0 || r >= ROWS || c < 0 || c >= COLS || n < 0 || n > NCH || !frep || !out || (n && !chs))
+  if (r < 0 || r >= ROWS || c < 0 || c >= COLS || n < 0 || n > NCH || !grid || !frep || !out || (n && !chs))
     return fail(h, DCA_ERR_ARG, "dca_gf_inc_afterstate_freps: bad argument");
   if (n == 0) return DCA_OK;
   for (int i = 0; i < n; ++i)
     if (chs[i] < 0 || chs[i] >= NCH) return fail(h, DCA_ERR_ARG, "dca_gf_inc_afterstate_freps: channel out of range");
-  GfScratch g;
-  int rc = gf_begin(device, grid, g);
+  OpScratch* sp = nullptr;
+  int rc = dev_scratch(device, &sp);
   if (rc) return rc;
-  CK(cudaMemcpy(g.frep, frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(g.chs, chs, sizeof(long long) * n, cudaMemcpyHostToDevice));
-  long long* d_out = nullptr;
-  CK(cudaMalloc(&d_out, sizeof(long long) * (size_t)n * FREP));
-  k_gf_inc_afterstate_freps<<<148, 256>>>(g.st, r * COLS + c, is_end, g.chs, n, g.frep, d_out);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(long long) * (size_t)n * FREP, cudaMemcpyDeviceToHost);
-  cudaFree(d_out);
-  if (e != cudaSuccess) return fail(h, DCA_ERR_CUDA, cudaGetErrorString(e));
-  return DCA_OK;
+  OpScratch& s = *sp;
+  std::lock_guard<std::mutex> lk(s.mu);
+  memcpy(s.h_io->grid, grid, DCA_GRID_SIZE);
+  memcpy(s.h_io->frep, frep, sizeof(int64_t) * FREP);
+  memcpy(s.h_io->chs, chs, sizeof(int64_t) * n);
+  if ((rc = io_h2d(s, IO_OFF(grid), IO_OFF(w))) || (rc = io_h2d(s, IO_OFF(frep), IO_OFF(nfrep))) ||
+      (rc = io_h2d(s, IO_OFF(chs), IO_OFF(out_frep))))
+    return rc;
+  launch_load_grid(s);
+  k_gf_inc_afterstate_freps<<<148, 256, 0, s.stream>>>(s.st, r * COLS + c, is_end, s.d_io->chs, n, s.d_io->frep, s.afreps);
+  CK(cudaGetLastError());
+  // (up to 1.9 MB straight into the caller's buffer: too large for the pinned mirror)
+  CK(cudaMemcpyAsync(out, s.afreps, sizeof(long long) * (size_t)n * FREP, cudaMemcpyDeviceToHost, s.stream));
+  return io_sync(s);
 }
 
 int dca_gf_violates_reuse_constraint(int32_t device, const uint8_t* grid, int32_t* violates) {
   dca_handle* h = nullptr;
-  if (!violates) return fail(h, DCA_ERR_ARG, "dca_gf_violates_reuse_constraint: null output");
-  GfScratch g;
-  int rc = gf_begin(device, grid, g);
+  if (!grid || !violates) return fail(h, DCA_ERR_ARG, "dca_gf_violates_reuse_constraint: null argument");
+  OpScratch* sp = nullptr;
+  int rc = dev_scratch(device, &sp);
   if (rc) return rc;
+  OpScratch& s = *sp;
+  std::lock_guard<std::mutex> lk(s.mu);
+  memcpy(s.h_io->grid, grid, DCA_GRID_SIZE);
+  if ((rc = io_h2d(s, IO_OFF(grid), IO_OFF(w)))) return rc;
+  launch_load_grid(s);
   CK(cudaFuncSetAttribute(k_gf_violates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-  k_gf_violates<<<1, 128, sizeof(Smem)>>>(g.st, g.n);
-  CK(cudaGetLastError());
-  int v = 0;
-  CK(cudaMemcpy(&v, g.n, sizeof(int), cudaMemcpyDeviceToHost));
-  *violates = v;
+  k_gf_violates<<<1, 128, sizeof(Smem), s.stream>>>(s.st, &s.d_io->violates);
+  if ((rc = io_d2h(s, IO_OFF(violates), IO_OFF(dot))) || (rc = io_sync(s))) return rc;
+  *violates = s.h_io->violates;
   return DCA_OK;
 }
-
-
-}  // extern "C"
 
 // ---- accFn1 / accFn2 on explicit arrays (SimRunner.hs:61-62) --------------------
-namespace {
-struct DevBuf {  // RAII device scratch
-  void* p = nullptr;
-  ~DevBuf() { cudaFree(p); }
-  template <typename T> T* as() { return static_cast<T*>(p); }
-};
-int dev_alloc(DevBuf& b, size_t bytes) {
-  dca_handle* h = nullptr;
-  CK(cudaMalloc(&b.p, bytes ? bytes : 1));
-  return DCA_OK;
-}
-}  // namespace
-
-extern "C" {
-
 int dca_acc_get_action(int32_t device, int32_t order, int32_t r, int32_t c, int32_t is_end, const float* wnet,
                        const uint8_t* grid, const int64_t* frep, int32_t* ch, int64_t* next_frep) {
   dca_handle* h = nullptr;
-  if (r < 0 || r >= ROWS || c < 0 || c >= COLS || !wnet || !frep || !ch || !next_frep ||
+  if (r < 0 || r >= ROWS || c < 0 || c >= COLS || !wnet || !grid || !frep || !ch || !next_frep ||
       (order != DCA_ORDER_REF && order != DCA_ORDER_FAST))
     return fail(h, DCA_ERR_ARG, "dca_acc_get_action: bad argument");
-  GfScratch g;
-  int rc = gf_begin(device, grid, g);
+  OpScratch* sp = nullptr;
+  int rc = dev_scratch(device, &sp);
   if (rc) return rc;
+  OpScratch& s = *sp;
+  std::lock_guard<std::mutex> lk(s.mu);
+  OpIO* d = s.d_io;
   const int cell = r * COLS + c;
-  k_gf_chs<<<1, 32>>>(g.st, cell, is_end, g.chs, g.n);  // eligibleChs / inuseChs, Simulator.hs:161-165
-  CK(cudaGetLastError());
-  int n = 0;
-  CK(cudaMemcpy(&n, g.n, sizeof(int), cudaMemcpyDeviceToHost));
-  if (n == 0) {  // (Nothing, frep), Simulator.hs:170-171
-    *ch = -1;
-    memcpy(next_frep, frep, sizeof(int64_t) * FREP);
-    return DCA_OK;
-  }
-  DevBuf afreps, w, q, idx;
-  if ((rc = dev_alloc(afreps, sizeof(long long) * (size_t)n * FREP)) || (rc = dev_alloc(w, sizeof(float) * FREP)) ||
-      (rc = dev_alloc(q, sizeof(float) * NCH)) || (rc = dev_alloc(idx, sizeof(int))))
+  memcpy(s.h_io->grid, grid, DCA_GRID_SIZE);
+  memcpy(s.h_io->w, wnet, sizeof(float) * FREP);
+  memcpy(s.h_io->frep, frep, sizeof(int64_t) * FREP);
+  if ((rc = io_h2d(s, IO_OFF(grid), IO_OFF(wg))) || (rc = io_h2d(s, IO_OFF(frep), IO_OFF(nfrep)))) return rc;
+  launch_load_grid(s);
+  k_gf_chs<<<1, 32, 0, s.stream>>>(s.st, cell, is_end, d->chs, &d->n);  // eligibleChs / inuseChs, Simulator.hs:161-165
+  // selectAction, Simulator.hs:185-205: afterstate freps -> q = mvMul -> argpmax; (Nothing, frep) without a candidate
+  ops::k_afterstates_dev<<<148, 256, 0, s.stream>>>(s.st, cell, is_end, d->chs, &d->n, d->frep, s.afreps);
+  ops::k_dense_dots_dev<<<NCH, ops::NT, 0, s.stream>>>(order, s.afreps, &d->n, d->w, s.q);
+  ops::k_select_dev<<<1, 256, 0, s.stream>>>(s.q, &d->n, d->chs, s.afreps, d->frep, &d->ch, d->out_frep);
+  if ((rc = io_d2h(s, IO_OFF(out_frep), IO_OFF(reward))) || (rc = io_d2h(s, IO_OFF(n), IO_OFF(dot))) || (rc = io_sync(s)))
     return rc;
-  CK(cudaMemcpy(g.frep, frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(w.p, wnet, sizeof(float) * FREP, cudaMemcpyHostToDevice));
-  // selectAction, Simulator.hs:185-205: afterstate freps -> q = mvMul -> argpmax
-  k_gf_inc_afterstate_freps<<<148, 256>>>(g.st, cell, is_end, g.chs, n, g.frep, afreps.as<long long>());
-  ops::k_dense_dots<<<n, ops::NT>>>(order, afreps.as<long long>(), n, w.as<float>(), q.as<float>());
-  ops::k_argpmax<<<1, 32>>>(q.as<float>(), n, idx.as<int>());
-  CK(cudaGetLastError());
-  int k = 0;
-  CK(cudaMemcpy(&k, idx.p, sizeof(int), cudaMemcpyDeviceToHost));
-  long long chs[NCH];
-  CK(cudaMemcpy(chs, g.chs, sizeof(long long) * n, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(next_frep, afreps.as<long long>() + (size_t)k * FREP, sizeof(long long) * FREP, cudaMemcpyDeviceToHost));
-  *ch = (int32_t)chs[k];
+  *ch = s.h_io->ch;
+  memcpy(next_frep, s.h_io->out_frep, sizeof(int64_t) * FREP);
   return DCA_OK;
 }
 
@@ -922,40 +1034,32 @@ int dca_acc_grid_step_train(int32_t device, int32_t order, float alpha_net, floa
   if (r < 0 || r >= ROWS || c < 0 || c >= COLS || ch >= NCH || !frep || !next_frep || !grid || !wnet || !wgrad ||
       !avg_reward || (order != DCA_ORDER_REF && order != DCA_ORDER_FAST))
     return fail(h, DCA_ERR_ARG, "dca_acc_grid_step_train: bad argument");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(h, DCA_ERR_NO_DEVICE, "dca_acc_grid_step_train: no CUDA device (there is no CPU fallback)");
-  int rc = set_device(h, device);
+  OpScratch* sp = nullptr;
+  int rc = dev_scratch(device, &sp);
   if (rc) return rc;
-  DevBuf dgrid, df, dnf, dw, dg, drew, dout;
-  if ((rc = dev_alloc(dgrid, DCA_GRID_SIZE)) || (rc = dev_alloc(df, sizeof(long long) * FREP)) ||
-      (rc = dev_alloc(dnf, sizeof(long long) * FREP)) || (rc = dev_alloc(dw, sizeof(float) * FREP)) ||
-      (rc = dev_alloc(dg, sizeof(float) * FREP)) || (rc = dev_alloc(drew, sizeof(long long))) ||
-      (rc = dev_alloc(dout, sizeof(ops::BackwardOut))))
-    return rc;
-  CK(cudaMemcpy(dgrid.p, grid, DCA_GRID_SIZE, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(df.p, frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dnf.p, next_frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dw.p, wnet, sizeof(float) * FREP, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dg.p, wgrad, sizeof(float) * FREP, cudaMemcpyHostToDevice));
+  OpScratch& s = *sp;
+  std::lock_guard<std::mutex> lk(s.mu);
+  OpIO* d = s.d_io;
+  memcpy(s.h_io->grid, grid, DCA_GRID_SIZE);
+  memcpy(s.h_io->w, wnet, sizeof(float) * FREP);
+  memcpy(s.h_io->wg, wgrad, sizeof(float) * FREP);
+  memcpy(s.h_io->frep, frep, sizeof(int64_t) * FREP);
+  memcpy(s.h_io->nfrep, next_frep, sizeof(int64_t) * FREP);
+  if ((rc = io_h2d(s, IO_OFF(grid), IO_OFF(chs)))) return rc;
   // gridStep, Simulator.hs:137-144
-  ops::k_grid_step<<<1, 256>>>(dgrid.as<uint8_t>(), r * COLS + c, is_end, ch, drew.as<long long>());
-  CK(cudaGetLastError());
-  long long rew = 0;
-  CK(cudaMemcpy(&rew, drew.p, sizeof rew, cudaMemcpyDeviceToHost));
+  ops::k_grid_step<<<1, 256, 0, s.stream>>>(d->grid, r * COLS + c, is_end, ch, &d->reward);
   // backward, Agent.hs:44-81 with reward' = fromIntegral reward (SimRunner.hs:117)
-  ops::k_backward<<<1, ops::NT>>>(order, alpha_net, alpha_avg, alpha_grad, df.as<long long>(), dnf.as<long long>(),
-                                  (float)rew, *avg_reward, dw.as<float>(), dg.as<float>(), dout.as<ops::BackwardOut>());
-  CK(cudaGetLastError());
-  ops::BackwardOut o;
-  CK(cudaMemcpy(&o, dout.p, sizeof o, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(grid, dgrid.p, DCA_GRID_SIZE, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(wnet, dw.p, sizeof(float) * FREP, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(wgrad, dg.p, sizeof(float) * FREP, cudaMemcpyDeviceToHost));
+  ops::k_backward_dev<<<1, ops::NT, 0, s.stream>>>(order, alpha_net, alpha_avg, alpha_grad, d->frep, d->nfrep, &d->reward,
+                                                   *avg_reward, d->w, d->wg, &d->bout);
+  if ((rc = io_d2h(s, IO_OFF(grid), IO_OFF(frep))) || (rc = io_d2h(s, IO_OFF(reward), IO_OFF(n))) || (rc = io_sync(s))) return rc;
+  memcpy(grid, s.h_io->grid, DCA_GRID_SIZE);
+  memcpy(wnet, s.h_io->w, sizeof(float) * FREP);
+  memcpy(wgrad, s.h_io->wg, sizeof(float) * FREP);
+  const ops::BackwardOut o = s.h_io->bout;
   *avg_reward = o.avg_reward;
   if (loss) *loss = o.loss;
   if (loss_is_nan) *loss_is_nan = o.loss_is_nan;
-  if (reward) *reward = rew;
+  if (reward) *reward = s.h_io->reward;
   return DCA_OK;
 }
 
@@ -963,23 +1067,87 @@ int dca_dense_dot(int32_t device, int32_t order, int32_t grad_corr_tree, const i
   dca_handle* h = nullptr;
   if (!frep || !w || !out || (order != DCA_ORDER_REF && order != DCA_ORDER_FAST))
     return fail(h, DCA_ERR_ARG, "dca_dense_dot: bad argument");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-    return fail(h, DCA_ERR_NO_DEVICE, "dca_dense_dot: no CUDA device (there is no CPU fallback)");
-  int rc = set_device(h, device);
+  OpScratch* sp = nullptr;
+  int rc = dev_scratch(device, &sp);
   if (rc) return rc;
-  DevBuf df, dw, dq;
-  if ((rc = dev_alloc(df, sizeof(long long) * FREP)) || (rc = dev_alloc(dw, sizeof(float) * FREP)) ||
-      (rc = dev_alloc(dq, sizeof(float))))
-    return rc;
-  CK(cudaMemcpy(df.p, frep, sizeof(long long) * FREP, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dw.p, w, sizeof(float) * FREP, cudaMemcpyHostToDevice));
-  if (grad_corr_tree) ops::k_dense_dot_g<<<1, ops::NT>>>(order, df.as<long long>(), dw.as<float>(), dq.as<float>());
-  else ops::k_dense_dots<<<1, ops::NT>>>(order, df.as<long long>(), 1, dw.as<float>(), dq.as<float>());
-  CK(cudaGetLastError());
-  CK(cudaMemcpy(out, dq.p, sizeof(float), cudaMemcpyDeviceToHost));
+  OpScratch& s = *sp;
+  std::lock_guard<std::mutex> lk(s.mu);
+  OpIO* d = s.d_io;
+  memcpy(s.h_io->w, w, sizeof(float) * FREP);
+  memcpy(s.h_io->frep, frep, sizeof(int64_t) * FREP);
+  if ((rc = io_h2d(s, IO_OFF(w), IO_OFF(wg))) || (rc = io_h2d(s, IO_OFF(frep), IO_OFF(nfrep)))) return rc;
+  if (grad_corr_tree) ops::k_dense_dot_g<<<1, ops::NT, 0, s.stream>>>(order, d->frep, d->w, &d->dot);
+  else ops::k_dense_dots<<<1, ops::NT, 0, s.stream>>>(order, d->frep, 1, d->w, &d->dot);
+  if ((rc = io_d2h(s, IO_OFF(dot), sizeof(OpIO))) || (rc = io_sync(s))) return rc;
+  *out = s.h_io->dot;
   return DCA_OK;
 }
+
+// ---- NCCL, resolved at call time with dlopen (no link-time dependency) -----------------
+// Communicators are created once per set of devices (ncclCommInitAll) and reused by later calls; a set whose
+// collective failed is destroyed and forgotten.  Every NCCL return code is checked.
+}  // extern "C"
+namespace {
+typedef void* nccl_comm_t;
+struct NcclComms {
+  std::vector<int> devs;
+  std::vector<nccl_comm_t> comms;
+};
+struct NcclApi {
+  std::mutex mu;
+  void* lib = nullptr;
+  int (*pInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+  int (*pAllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+  int (*pGroupStart)() = nullptr;
+  int (*pGroupEnd)() = nullptr;
+  int (*pDestroy)(nccl_comm_t) = nullptr;
+  std::vector<NcclComms> cache;
+
+  const char* load() {
+    if (lib) return nullptr;
+    void* l = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!l) l = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!l) return "dca_allreduce_stats: libnccl.so.2 not found";
+    pInitAll = (int (*)(nccl_comm_t*, int, const int*))dlsym(l, "ncclCommInitAll");
+    pAllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(l, "ncclAllReduce");
+    pGroupStart = (int (*)())dlsym(l, "ncclGroupStart");
+    pGroupEnd = (int (*)())dlsym(l, "ncclGroupEnd");
+    pDestroy = (int (*)(nccl_comm_t))dlsym(l, "ncclCommDestroy");
+    if (!pInitAll || !pAllReduce || !pGroupStart || !pGroupEnd || !pDestroy) {
+      dlclose(l);
+      return "dca_allreduce_stats: NCCL symbols missing";
+    }
+    lib = l;
+    return nullptr;
+  }
+  const char* comms_for(const std::vector<int>& devs, NcclComms** out) {
+    for (NcclComms& c : cache)
+      if (c.devs == devs) { *out = &c; return nullptr; }
+    NcclComms c;
+    c.devs = devs;
+    c.comms.assign(devs.size(), nullptr);
+    if (pInitAll(c.comms.data(), (int)devs.size(), devs.data()) != 0) {
+      for (nccl_comm_t x : c.comms)
+        if (x) pDestroy(x);
+      return "dca_allreduce_stats: ncclCommInitAll failed";
+    }
+    cache.push_back(std::move(c));
+    *out = &cache.back();
+    return nullptr;
+  }
+  void drop(const std::vector<int>& devs) {
+    for (size_t i = 0; i < cache.size(); ++i)
+      if (cache[i].devs == devs) {
+        for (nccl_comm_t x : cache[i].comms)
+          if (x) pDestroy(x);
+        cache.erase(cache.begin() + i);
+        return;
+      }
+  }
+};
+NcclApi g_nccl;
+}  // namespace
+extern "C" {
 
 // ---- multi-GPU stats reduction over NCCL (single process, many handles) --------
 // NCCL is resolved at call time with dlopen so that the library has no link-time
@@ -989,41 +1157,44 @@ int dca_allreduce_stats(dca_handle** handles, int32_t n, int64_t out[10]) {
   dca_handle* h = (handles && n > 0) ? handles[0] : nullptr;
   if (!h || !out) return fail(h, DCA_ERR_ARG, "dca_allreduce_stats: bad argument");
   for (int i = 0; i < n; ++i) {
+    if (!handles[i]) return fail(h, DCA_ERR_ARG, "dca_allreduce_stats: null handle");
     int rc = dca_sum_stats(handles[i], nullptr, nullptr);
     if (rc) return rc;
   }
   if (n == 1) return dca_sum_stats(h, out, nullptr);
-  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-  if (!lib) return fail(h, DCA_ERR_STATE, "dca_allreduce_stats: libnccl.so.2 not found");
-  typedef void* comm_t;
-  auto pInitAll = (int (*)(comm_t*, int, const int*))dlsym(lib, "ncclCommInitAll");
-  auto pAllReduce = (int (*)(const void*, void*, size_t, int, int, comm_t, cudaStream_t))dlsym(lib, "ncclAllReduce");
-  auto pGroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
-  auto pGroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
-  auto pDestroy = (int (*)(comm_t))dlsym(lib, "ncclCommDestroy");
-  if (!pInitAll || !pAllReduce || !pGroupStart || !pGroupEnd || !pDestroy)
-    return fail(h, DCA_ERR_STATE, "dca_allreduce_stats: NCCL symbols missing");
-  std::vector<comm_t> comms(n);
   std::vector<int> devs(n);
   for (int i = 0; i < n; ++i) devs[i] = handles[i]->device;
-  if (pInitAll(comms.data(), n, devs.data()) != 0) return fail(h, DCA_ERR_STATE, "ncclCommInitAll failed");
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j)
+      if (devs[i] == devs[j]) return fail(h, DCA_ERR_ARG, "dca_allreduce_stats: two handles on the same device (NCCL needs one rank per device)");
+  std::lock_guard<std::mutex> lk(g_nccl.mu);
+  const char* err = g_nccl.load();
+  if (err) return fail(h, DCA_ERR_STATE, err);
+  NcclComms* cs = nullptr;
+  if ((err = g_nccl.comms_for(devs, &cs))) return fail(h, DCA_ERR_STATE, err);
   const int ncclInt64 = 4, ncclSum = 0;
-  pGroupStart();
-  for (int i = 0; i < n; ++i) {
-    cudaSetDevice(devs[i]);
-    pAllReduce(handles[i]->d_sum, handles[i]->d_sum, 10, ncclInt64, ncclSum, comms[i], handles[i]->stream);
+  int bad = 0, rc_nccl = g_nccl.pGroupStart();
+  if (rc_nccl == 0) {
+    for (int i = 0; i < n && !bad; ++i) {
+      if (cudaSetDevice(devs[i]) != cudaSuccess) { bad = -1; break; }
+      bad = g_nccl.pAllReduce(handles[i]->d_sum, handles[i]->d_sum, 10, ncclInt64, ncclSum, cs->comms[i], handles[i]->stream);
+    }
+    rc_nccl = g_nccl.pGroupEnd();  // (always closes the group that was opened)
   }
-  if (pGroupEnd() != 0) return fail(h, DCA_ERR_STATE, "ncclAllReduce failed");
+  if (rc_nccl != 0 || bad != 0) {
+    g_nccl.drop(devs);  // a failed collective leaves the communicators unusable: destroy them
+    return fail(h, DCA_ERR_STATE, "dca_allreduce_stats: ncclAllReduce failed");
+  }
   for (int i = 0; i < n; ++i) {
-    cudaSetDevice(devs[i]);
-    cudaStreamSynchronize(handles[i]->stream);
+    if (cudaSetDevice(devs[i]) != cudaSuccess || cudaStreamSynchronize(handles[i]->stream) != cudaSuccess) {
+      g_nccl.drop(devs);
+      return fail(h, DCA_ERR_CUDA, "dca_allreduce_stats: stream synchronisation after the all-reduce failed");
+    }
   }
   long long tmp[10];
-  cudaSetDevice(devs[0]);
+  CK(cudaSetDevice(devs[0]));
   CK(cudaMemcpy(tmp, h->d_sum, sizeof tmp, cudaMemcpyDeviceToHost));
   for (int k = 0; k < 10; ++k) out[k] = tmp[k];
-  for (int i = 0; i < n; ++i) pDestroy(comms[i]);
   return DCA_OK;
 }
 

@@ -928,6 +928,7 @@ __device__ __forceinline__ void ev_prepare(SmemF& sm, EvRegs& e, const Ev& ev) {
 // the next event (ev_env_pop) -- neither depends on WHICH channel was chosen, only on whether the
 // call was accepted -- and the channel-dependent rest (ev_env_post: END key, reassign, grid bit).
 constexpr int CH_PENDING = 127;  // channel of the END event pushed by the current event: not chosen yet
+constexpr int PEND_OVERFLOW = -2;  // ev_env_push: the END event did not fit into the slot table
 struct EnvNext {                 // the next event (registers, warp-uniform)
   double time;
   int type, cell, ch, hoff;
@@ -1005,8 +1006,13 @@ __device__ __forceinline__ int ev_env_push(SmemF& sm, EvRegs& e, const int type,
       }
       q_block_push(sm, slot, t_end, id_end);
       pend_slot = (int)slot;
+      e.n_end++;
+    } else {
+      // the table is full (more than QEND calls in progress: impossible while the reuse constraint holds, reachable
+      // only from a grid forced in through dca_write_state): nothing is written, n_end stays in bounds, and the
+      // caller stops the replica with ST_QUEUE_OVERFLOW
+      pend_slot = PEND_OVERFLOW;
     }
-    e.n_end++;
   }
   __syncwarp();
   return pend_slot;
@@ -1356,7 +1362,9 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
     if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);  // executeAction, Gridfuncs.hs:105-110
-    const int pend_slot = ev_env_push(sm, e, type, cell, time, n > 0);       // Simulator.hs:101-128: new events
+    const int pushed = ev_env_push(sm, e, type, cell, time, n > 0);         // Simulator.hs:101-128: new events
+    const bool q_overflow = pushed == PEND_OVERFLOW;
+    const int pend_slot = q_overflow ? -1 : pushed;
     const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
     // the candidate list of the next event needs its kind and cell, the grid and cnt2: all known here
     if (lane == 0) { nx.type = en.type; nx.cell = en.cell; }
@@ -1372,6 +1380,7 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
       e.loss_sum = __fadd_rn(e.loss_sum, d.tderr);
       e.loss_n += 1;
     }
+    if (stop == ST_RUNNING && q_overflow) stop = ST_QUEUE_OVERFLOW;
     if (sync_end) {
       cta_barrier();  // the agents have moved frep to the afterstate
       if (stop == ST_RUNNING && (a.verify_rc || a.verify_nb)) {
@@ -1479,14 +1488,28 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
     if (lane == 0) { ev.cell = cell; ev.type = is_end ? EV_END : EV_NEW; }
     __syncwarp();
     ev_candidates(sm, ev, -1);
-    if (mode == 1 && lane == 0) {  // evaluate exactly the channel the caller executes
-      ev.ncand = ch_in >= 0 ? 1 : 0;
-      ev.cand[0] = (uint8_t)(ch_in >= 0 ? ch_in : 0);
+    if (mode == 1) {  // evaluate exactly the channel the caller executes -- it must be one getAction could have returned
+      bool found = ch_in < 0;
+      for (int k = lane; k < ev.ncand; k += 32) found |= ev.cand[k] == ch_in;
+      found = __any_sync(0xffffffffu, found);
+      __syncwarp();
+      if (lane == 0) {
+        sm.status = found ? 0 : -1;
+        ev.ncand = ch_in >= 0 ? 1 : 0;
+        ev.cand[0] = (uint8_t)(ch_in >= 0 ? ch_in : 0);
+      }
+    } else if (lane == 0) {
+      sm.status = 0;
     }
   } else {
     dense_pass<false>(sm, ag, l, -1, false, TdScalars{0.f, 0.f, 0.f, 0.f}, make_uint2(0, 0), make_uint2(0, 0));
   }
   __syncthreads();
+  if (sm.status != 0) {  // (uniform) the channel is not eligible / not in use at this cell: nothing is changed
+    if (threadIdx.x == 0) out->ch = STEP_BAD_CHANNEL;
+    tmem_close(sm);
+    return;
+  }
   const int n = ev.ncand;
   const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
   const VTree vt = wid != EVW ? q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r) : v_tree(sm);
@@ -1502,7 +1525,11 @@ __global__ void __launch_bounds__(NT) k_step_fast(RepState* states, int rep, int
   dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
   const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
   if (wid == EVW) {
-    if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);
+    if (lane == 0 && d.act >= 0) {  // executeAction, Gridfuncs.hs:105-110
+      const uint32_t bit = 1u << (d.act & 31);
+      if (is_end) sm.grid[cell][d.act >> 5] &= ~bit;
+      else sm.grid[cell][d.act >> 5] |= bit;
+    }
   } else {
     dense_pass<true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
   }

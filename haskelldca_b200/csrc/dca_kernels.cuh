@@ -191,6 +191,7 @@ struct Rng {
 // ---------------------------------------------------------------------------
 struct QRegs {
   unsigned n_end, next_id;
+  bool overflow = false;  // an END event did not fit (more than QEND calls in progress): the replica stops
 };
 
 __device__ __forceinline__ void q_push_new(RepState& s, QRegs& q, int cell, double t) {
@@ -203,7 +204,12 @@ __device__ __forceinline__ void q_push_new(RepState& s, QRegs& q, int cell, doub
 __device__ __forceinline__ void q_push_end(RepState& s, QRegs& q, int cell, int ch, int hoff,
                                            double t) {
   unsigned slot = QNEW + q.n_end;
-  if (lane_id() == 0 && slot < QCAP) {
+  if (slot >= QCAP) {  // (uniform) the table is full: nothing is written, n_end stays in bounds
+    q.overflow = true;
+    q.next_id++;
+    return;
+  }
+  if (lane_id() == 0) {
     s.q_time[slot] = t;
     s.q_id[slot] = q.next_id;
     s.q_key[slot] = (uint16_t)((cell << 7) | ch);
@@ -666,6 +672,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
         s.loss_sum = __fadd_rn(s.loss_sum, td);
         s.loss_n += 1;
       }
+      if (stop == ST_RUNNING && q.overflow) stop = ST_QUEUE_OVERFLOW;
       t.stop = stop;
     }
   }
@@ -721,7 +728,7 @@ __global__ void __launch_bounds__(128) k_run(RunArgs a) {
   stage_in(sm, g);
   __syncthreads();
   if (!sm.s.initialized || sm.s.status != ST_RUNNING) return;  // uniform
-  QRegs q{sm.s.n_end, sm.s.next_id};
+  QRegs q{sm.s.n_end, sm.s.next_id, false};
   Rng rng = make_rng(a, sm.s, rep);
   for (long long it = 0; it < a.max_events; ++it) {
     run_event<ORDER, TRACE>(sm, a, q, rng, rep);
@@ -797,11 +804,11 @@ __global__ void k_init(InitArgs a) {
   const bool have_rng = a.rng_mode == RNG_PHILOX ||
                         (a.tape_off && a.tape_off[rep + 1] - a.tape_off[rep] >= (unsigned long long)NCELL);
   if (!have_rng) {  // tape not set yet: stays uninitialised
-    if (lane == 0) s.initialized = 0;
+    if (lane == 0) { s.initialized = 0; s.status = ST_UNINITIALIZED; }
     return;
   }
   Rng rng = make_rng(ra, s, rep);
-  QRegs q{0u, 0u};
+  QRegs q{0u, 0u, false};
   // mkEventGen (EventGen.hs:54-58): one NEW per cell, row-major, at 0 + Exp(mean_new)
   for (int cell = 0; cell < NCELL; ++cell) {
     double dt = rng.exponential(s.mean_new);
@@ -861,6 +868,7 @@ __global__ void k_feature_rep(RepState* states, int rep) {
 // ---------------------------------------------------------------------------
 // Step-wise operators on one replica: accFn1 / accFn2 (SimRunner.hs:61-62).
 // ---------------------------------------------------------------------------
+constexpr int STEP_BAD_CHANNEL = -3;  // StepOut.ch: gridStepTrain was given a channel getAction could not have returned
 struct StepOut {
   int ch;
   int loss_is_nan;
@@ -884,8 +892,13 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   __syncthreads();
   if (wid == 0) {
     const int n = build_candidates(sm, cell, is_end);
+    bool found = mode == 0 || ch_in < 0;  // the channel must be one getAction could have returned at this cell
+    for (int k = lane; k < n; k += 32) found |= t.cand[k] == ch_in;
+    found = __any_sync(0xffffffffu, found);
+    __syncwarp();
     if (lane == 0) {
       t.ncand = n;
+      t.flag = found ? 0 : 1;
       if (mode == 1) {  // evaluate exactly the channel the caller executes
         t.ncand = ch_in >= 0 ? 1 : 0;
         t.cand[0] = (uint8_t)(ch_in >= 0 ? ch_in : 0);
@@ -893,6 +906,10 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
     }
   }
   __syncthreads();
+  if (t.flag) {  // (uniform) nothing is changed
+    if (threadIdx.x == 0) out->ch = STEP_BAD_CHANNEL;
+    return;
+  }
   const int n = t.ncand;
   {
     for (int k = threadIdx.x; k < n; k += nthreads - 2)
@@ -1063,7 +1080,7 @@ __global__ void k_summary(const RepState* states, int n, Summary* out) {
   if (i >= n) return;
   const RepState& s = states[i];
   Summary o;
-  o.status = s.initialized ? s.status : ST_RUNNING;
+  o.status = s.initialized ? s.status : ST_UNINITIALIZED;
   o.pad = 0;
   o.iter = s.iter;
   o.avg_reward = s.avg_reward;

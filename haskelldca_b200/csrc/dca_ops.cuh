@@ -114,6 +114,50 @@ __global__ void k_argpmax(const float* q, int n, int* idx) {
   }
 }
 
+// ---- accFn1 as one stream of launches without a host round trip: the candidate count stays on the device ----
+// incAfterStateFreps for the candidates k_gf_chs found (count read from *n_dev)
+__global__ void k_afterstates_dev(const RepState* st, int cell, int is_end, const long long* chs, const int* n_dev,
+                                  const long long* frep, long long* out) {
+  const int n = *n_dev;
+  const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
+  const int diff = is_end ? -1 : 1;
+  const uint8_t want = is_end ? 1 : 0;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)n * FREP;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(idx / FREP), i = (int)(idx - (long long)k * FREP);
+    const int c2 = i / NFEAT, f = i - c2 * NFEAT;
+    const int ch = (int)chs[k];
+    long long v = frep[i];  // Gridfuncs.hs:206
+    if (f == ch && ((n4 >> c2) & 1ULL)) v += diff;                                                       // :212-217
+    if (f == NCH && ((n2 >> c2) & 1ULL) && st->cnt2[ch * PLANE + c_tab.pos[c2]] == want) v -= diff;      // :220-252
+    out[idx] = v;
+  }
+}
+// mvMul (src/AccUtils.hs:224-228): one CTA per candidate, NCH CTAs launched
+__global__ void __launch_bounds__(NT) k_dense_dots_dev(int order, const long long* freps, const int* n_dev, const float* w, float* q) {
+  __shared__ DotScratch t;
+  const int k = blockIdx.x;
+  if (k >= *n_dev) return;
+  const float v = cta_dense_dot(t, order, false, freps + (size_t)k * FREP, w);
+  if (threadIdx.x == 0) q[k] = v;
+}
+// argpmax + the result of getAction (src/Simulator.hs:165-172, 202-205): (Just chs[idx], afreps[idx]) or (Nothing, frep)
+__global__ void k_select_dev(const float* q, const int* n_dev, const long long* chs, const long long* afreps,
+                             const long long* frep, int* ch_out, long long* frep_out) {
+  __shared__ int best_s;
+  const int n = *n_dev;
+  if (threadIdx.x == 0) {
+    int best = n - 1;
+    for (int i = n - 2; i >= 0; --i)
+      if (q[i] > q[best]) best = i;
+    best_s = best;
+    *ch_out = n > 0 ? (int)chs[best] : -1;
+  }
+  __syncthreads();
+  const long long* src = n > 0 ? afreps + (size_t)best_s * FREP : frep;
+  for (int i = threadIdx.x; i < FREP; i += blockDim.x) frep_out[i] = src[i];
+}
+
 struct BackwardOut {
   float loss;
   int loss_is_nan;
@@ -122,10 +166,9 @@ struct BackwardOut {
 };
 
 // backward (src/Agent.hs:44-81) on explicit arrays; w, wg updated in place
-__global__ void __launch_bounds__(NT) k_backward(int order, float alpha_net, float alpha_avg, float alpha_grad,
-                                                 const long long* frep, const long long* next_frep, float reward,
-                                                 float avg_reward, float* w, float* wg, BackwardOut* out) {
-  __shared__ DotScratch t;
+__device__ __forceinline__ void backward_body(DotScratch& t, int order, float alpha_net, float alpha_avg, float alpha_grad,
+                                              const long long* frep, const long long* next_frep, float reward,
+                                              float avg_reward, float* w, float* wg, BackwardOut* out) {
   const float val = cta_dense_dot(t, order, false, frep, w);           // :62
   const float next_val = cta_dense_dot(t, order, false, next_frep, w); // :63
   const float dot = cta_dense_dot(t, order, true, frep, wg);           // :66
@@ -151,6 +194,20 @@ __global__ void __launch_bounds__(NT) k_backward(int order, float alpha_net, flo
     out->avg_reward = __fadd_rn(avg_reward, __fmul_rn(alpha_avg, td));  // :78
     out->pad = 0;
   }
+}
+__global__ void __launch_bounds__(NT) k_backward(int order, float alpha_net, float alpha_avg, float alpha_grad,
+                                                 const long long* frep, const long long* next_frep, float reward,
+                                                 float avg_reward, float* w, float* wg, BackwardOut* out) {
+  __shared__ DotScratch t;
+  backward_body(t, order, alpha_net, alpha_avg, alpha_grad, frep, next_frep, reward, avg_reward, w, wg, out);
+}
+// gridStepTrain's second half with the reward still on the device (reward' = fromIntegral reward, SimRunner.hs:117)
+__global__ void __launch_bounds__(NT) k_backward_dev(int order, float alpha_net, float alpha_avg, float alpha_grad,
+                                                     const long long* frep, const long long* next_frep,
+                                                     const long long* reward_dev, float avg_reward, float* w, float* wg,
+                                                     BackwardOut* out) {
+  __shared__ DotScratch t;
+  backward_body(t, order, alpha_net, alpha_avg, alpha_grad, frep, next_frep, (float)*reward_dev, avg_reward, w, wg, out);
 }
 
 // executeAction (src/Gridfuncs.hs:105-110) on a byte grid + boolSum (src/AccUtils.hs:166-167)

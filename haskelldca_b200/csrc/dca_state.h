@@ -36,7 +36,9 @@ constexpr int HOFF_NONE = 255;
 
 enum { EV_NEW = 0, EV_END = 1, EV_HOFF = 2 };
 enum { ST_RUNNING = 0, ST_SUCCESS, ST_ZERO_LOSS, ST_NAN_LOSS, ST_REUSE_VIOLATED,
-       ST_NELIG_OVERFLOW, ST_TAPE_EXHAUSTED };
+       ST_NELIG_OVERFLOW, ST_TAPE_EXHAUSTED,
+       ST_UNINITIALIZED,    // DCA_RNG_TAPE replica whose tape has not been set (or is shorter than the 49 initial draws)
+       ST_QUEUE_OVERFLOW }; // more than QEND calls in progress: only reachable from a state that violates the reuse constraint
 enum { ORDER_REF = 0, ORDER_FAST = 1 };
 enum { RNG_TAPE = 0, RNG_PHILOX = 1 };
 

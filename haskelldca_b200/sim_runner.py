@@ -14,7 +14,8 @@ from .simulator import Replicas
 SIM_STOP = {  # SimStop, SimRunner.hs:45-50
     _ffi.RUNNING: "Paused", _ffi.SUCCESS: "Success", _ffi.ZERO_LOSS: "ZeroLoss", _ffi.NAN_LOSS: "NaNLoss",
     _ffi.REUSE_VIOLATED: "InternalError ReuseConstraintViolated", _ffi.NELIG_OVERFLOW: "InternalError NEligOverflow",
-    _ffi.TAPE_EXHAUSTED: "InternalError TapeExhausted",
+    _ffi.TAPE_EXHAUSTED: "InternalError TapeExhausted", _ffi.UNINITIALIZED: "InternalError Uninitialized",
+    _ffi.QUEUE_OVERFLOW: "InternalError EventQueueOverflow",
 }
 
 
@@ -24,10 +25,13 @@ def run_sim(opt: Opt, out=print, replica: int = 0):
     sims = Replicas(opt)
     try:
         device_ms = 0.0
-        status = _ffi.RUNNING
+        status, last_it = _ffi.RUNNING, -1
         while status == _ffi.RUNNING:
             device_ms += sims.run(opt.log_iter)  # one period (SimRunner.hs:167-168)
             status, it, _ = sims.read_status(replica)
+            if it == last_it:  # a period without progress can only be a library fault: never spin on it
+                raise _ffi.DcaError(f"replica {replica} made no progress in a period (status {status}, iter {it})")
+            last_it = it
             st = sims.read_stats(replica)
             loss_sum, loss_n = sims.read_period(replica, reset=True)
             avg = sims.read_state(replica)["avg_reward"] if opt.n_replicas == 1 else sims.read_summary()["avg_reward"][replica]

@@ -212,3 +212,15 @@ class Replicas:
         dev = C.c_void_p()
         _ffi.check(_ffi.load().dca_sum_stats(self.h, _ffi.ptr(out), C.byref(dev)), self.h)
         return out, dev.value
+
+
+def allreduce_stats(replica_sets) -> np.ndarray:
+    """dca_allreduce_stats: the int64[10] of `sum_stats` summed over several `Replicas` of THIS process, one per
+    device, with ncclAllReduce over NVLink (the only collective of the path: the blocking-probability counters,
+    src/Stats.hs:83-92).  With one process per GPU all-reduce `sum_stats()[1]` with the process group instead."""
+    L = _ffi.load()
+    n = len(replica_sets)
+    arr = (C.c_void_p * n)(*[s.h for s in replica_sets])
+    out = np.zeros(10, dtype=np.int64)
+    _ffi.check(L.dca_allreduce_stats(arr, n, _ffi.ptr(out)), replica_sets[0].h)
+    return out

@@ -182,6 +182,8 @@ inline const char* simStop(int status) {
     case DCA_REUSE_VIOLATED: return "InternalError ReuseConstraintViolated";
     case DCA_NELIG_OVERFLOW: return "InternalError NEligOverflow";
     case DCA_TAPE_EXHAUSTED: return "InternalError TapeExhausted";
+    case DCA_UNINITIALIZED: return "InternalError Uninitialized";
+    case DCA_QUEUE_OVERFLOW: return "InternalError EventQueueOverflow";
   }
   return "?";
 }
@@ -277,10 +279,14 @@ inline int runSim(const Opt& opt, const std::function<void(const std::string&)>&
   const auto t0 = std::chrono::steady_clock::now();
   Replicas sims(opt);
   int status = DCA_RUNNING;
+  long long lastIter = -1;
   while (status == DCA_RUNNING) {
     sims.run(opt.logIter);  // one period (SimRunner.hs:167-168)
     const Replicas::Status st = sims.status(0);
     status = st.status;
+    if (st.iter == lastIter)  // a period without progress can only be a library fault: never spin on it
+      throw std::runtime_error(fmt("replica 0 made no progress in a period (status %d, iter %lld)", status, st.iter));
+    lastIter = st.iter;
     int64_t counters[DCA_N_STATS];
     sims.stats(0, counters);
     const Replicas::Period p = sims.period(0, true);

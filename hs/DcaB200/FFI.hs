@@ -75,6 +75,8 @@ foreign import ccall safe "dca_read_status" c_dca_read_status
   :: Ptr DcaHandle -> Int32 -> Ptr Int32 -> Ptr Int64 -> Ptr Word64 -> IO CInt
 foreign import ccall safe "dca_read_period" c_dca_read_period
   :: Ptr DcaHandle -> Int32 -> Ptr CFloat -> Ptr Int64 -> Int32 -> IO CInt
+foreign import ccall safe "dca_read_summary" c_dca_read_summary
+  :: Ptr DcaHandle -> Ptr Int32 -> Ptr Int64 -> Ptr CFloat -> Ptr Int64 -> IO CInt
 foreign import ccall safe "dca_sum_stats" c_dca_sum_stats :: Ptr DcaHandle -> Ptr Int64 -> Ptr (Ptr ()) -> IO CInt
 foreign import ccall safe "dca_allreduce_stats" c_dca_allreduce_stats
   :: Ptr (Ptr DcaHandle) -> Int32 -> Ptr Int64 -> IO CInt

@@ -71,6 +71,9 @@ extern "C" {
 #define DCA_REUSE_VIOLATED 4
 #define DCA_NELIG_OVERFLOW 5
 #define DCA_TAPE_EXHAUSTED 6 /* DCA_RNG_TAPE ran out of words */
+#define DCA_UNINITIALIZED 7  /* DCA_RNG_TAPE replica without a tape yet: dca_run refuses to start (DCA_ERR_STATE) */
+#define DCA_QUEUE_OVERFLOW 8 /* > 630 calls in progress: impossible while the reuse constraint holds (9 co-channel
+                                cells x 70 channels); reachable only from a grid forced in with dca_write_state */
 
 /* stats counters, src/Stats.hs:15-30 */
 #define DCA_ST_ARRIVALS_NEW 0
@@ -175,7 +178,9 @@ int dca_get_action(dca_handle *h, int32_t replica, int32_t r, int32_t c, int32_t
                    int32_t *ch);
 /* gridStepTrain (src/SimRunner.hs:100-118): execute the action on the grid,
  * reward = calls in progress, average-reward TDC update (src/Agent.hs:44-81),
- * then frep := nextFrep (src/SimRunner.hs:88-90). */
+ * then frep := nextFrep (src/SimRunner.hs:88-90).  ch must be a channel getAction could have
+ * returned for this event (eligible at the cell, or in use there for an END) or -1 (Nothing);
+ * anything else is DCA_ERR_ARG and changes nothing. */
 int dca_grid_step_train(dca_handle *h, int32_t replica, float alpha_net, float alpha_avg,
                         float alpha_grad, int32_t is_end, int32_t r, int32_t c, int32_t ch,
                         float *loss, int32_t *loss_is_nan, int64_t *reward);
@@ -206,7 +211,10 @@ int dca_dense_dot(int32_t device, int32_t order, int32_t grad_corr_tree, const i
 int dca_read_state(dca_handle *h, int32_t replica, uint8_t *grid, int64_t *frep, float *wnet,
                    float *wgrad, float *avg_reward, int64_t *iter, dca_event *next_event);
 /* overwrite grid and/or agent; frep is recomputed with featureRep (src/Gridfuncs.hs:153-170).
- * Pending END events are NOT rebuilt: meant for step-wise use and tests. */
+ * The event queue is NOT rebuilt: after a grid write it no longer matches the calls in progress
+ * (an END event of a removed call would find no channel; a grid that violates the reuse constraint
+ * can exceed the queue's 630 slots, which dca_run reports as DCA_QUEUE_OVERFLOW).  Meant for the
+ * step-wise operators, warm-started weights and tests. */
 int dca_write_state(dca_handle *h, int32_t replica, const uint8_t *grid, const float *wnet,
                     const float *wgrad, const float *avg_reward);
 int dca_read_stats(dca_handle *h, int32_t replica, int64_t stats[DCA_N_STATS]);
@@ -229,7 +237,9 @@ void dca_stats_cumus(const int64_t stats[DCA_N_STATS], double out3[3]);
 /* ---- checkpoint / resume (absent in the reference) ------------------ */
 /* The complete simulator state of every replica (grid, frep, agent, event queue, RNG position,
  * statistics) as one opaque blob of dca_checkpoint_size(h) bytes.  A blob can be loaded into any
- * handle created with the same n_replicas, order and rng_mode; running on continues bit for bit. */
+ * handle created with the same n_replicas, order, rng_mode, seed and first_replica (and, in
+ * DCA_RNG_TAPE mode, the same tapes) -- the random stream lives in the handle, so only then does
+ * running on continue bit for bit; anything else is rejected with DCA_ERR_STATE. */
 size_t dca_checkpoint_size(const dca_handle *h);
 int dca_checkpoint_save(dca_handle *h, void *buf, size_t size);
 int dca_checkpoint_load(dca_handle *h, const void *buf, size_t size);

@@ -99,19 +99,20 @@ def test_run_in_periods_equals_one_run():
         assert sims.read_status(0)[1] == n
 
 
-@pytest.mark.parametrize("warps", [1, 2, 4])
-def test_philox_replicas_match_oracle(warps):
-    """Config 3's RNG mode on a small batch: every replica equals its own oracle run, for any CTA width."""
+@pytest.mark.parametrize("first,seed", [(0, 42), (1000, 42), ((1 << 33) + 5, (7 << 32) | 3)])
+def test_philox_replicas_match_oracle(first, seed):
+    """Config 3's RNG mode on a small batch: every replica equals its own oracle run; the Philox stream id
+    (first_replica + r) and the key (seed) are 64-bit quantities."""
     from haskelldca_b200 import Opt, Replicas
 
     n_rep, n_ev = 24, 1500
-    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=42, hoff_prob=0.15,
-                      first_replica=1000, trace=n_ev, warps_per_replica=warps)) as sims:
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=seed, hoff_prob=0.15,
+                      first_replica=first, trace=n_ev)) as sims:
         sims.run(n_ev)
         summ = sims.read_summary()
         assert (summ["status"] == po.SUCCESS).all() and (summ["iter"] == n_ev).all()
         for r in range(n_rep):
-            o, _, tr = oracle_run(po.ORDER_FAST, n_ev, seed=42, hoff=0.15, rng=po.RNG_PHILOX, replica=1000 + r)
+            o, _, tr = oracle_run(po.ORDER_FAST, n_ev, seed=seed, hoff=0.15, rng=po.RNG_PHILOX, replica=first + r)
             assert_trace_equal(sims.read_trace(r), tr)
             assert_state_equal(sims.read_state(r), o.read())
         total, dev = sims.sum_stats()
@@ -381,3 +382,77 @@ def test_randomised_parameters_and_chunked_runs_match_the_oracle():
                 assert len(tr) == n_done
                 assert_trace_equal(sims.read_trace(r), tr)
                 assert_state_equal(sims.read_state(r), o.read())
+
+
+def test_guard_rails_of_the_c_abi():
+    """Library faults are errors or dedicated status words, never a silent spin or an out-of-bounds write."""
+    from haskelldca_b200 import Opt, Replicas, _ffi
+    from haskelldca_b200._ffi import DcaError
+
+    # a DCA_RNG_TAPE replica without a tape is DCA_UNINITIALIZED and dca_run refuses to start
+    L = _ffi.load()
+    import ctypes as C
+    cfg = _ffi.Config()
+    _ffi.check(L.dca_config_defaults(C.byref(cfg)))
+    cfg.n_replicas, cfg.rng_mode, cfg.n_events = 2, _ffi.RNG_TAPE, 100
+    h = C.c_void_p()
+    _ffi.check(L.dca_create(C.byref(cfg), C.byref(h)))
+    try:
+        st = np.zeros(2, np.int32)
+        _ffi.check(L.dca_read_summary(h, _ffi.ptr(st), None, None, None), h)
+        assert (st == _ffi.UNINITIALIZED).all()
+        _ffi.check(L.dca_set_rng_mt19937(h, 0, 0, 1000), h)  # replica 1 still has none
+        assert L.dca_run(h, 10) == -4  # DCA_ERR_STATE
+        assert b"replica 1 has no random tape" in L.dca_last_error(h)
+        _ffi.check(L.dca_set_rng_mt19937(h, 1, 1, 1000), h)
+        _ffi.check(L.dca_run(h, 10), h)
+        _ffi.check(L.dca_read_summary(h, _ffi.ptr(st), None, None, None), h)
+        assert (st == _ffi.RUNNING).all()
+    finally:
+        L.dca_destroy(h)
+
+    # gridStepTrain only executes a channel getAction could have returned; a bad one changes nothing
+    for order in ("fast", "ref"):
+        with Replicas(Opt(n_events=100, order=order)) as sims:
+            ch = sims.get_action(0, (3, 3), False)
+            sims.grid_step_train(0, False, (3, 3), ch)
+            before = sims.read_state(0)
+            with pytest.raises(DcaError):
+                sims.grid_step_train(0, False, (3, 4), ch)      # in use one cell away: not eligible
+            with pytest.raises(DcaError):
+                sims.grid_step_train(0, True, (3, 3), (ch + 1) % 70)  # not in use at the cell
+            after = sims.read_state(0)
+            assert np.array_equal(before["grid"], after["grid"]) and np.array_equal(bits(before["w"]), bits(after["w"]))
+            sims.grid_step_train(0, True, (3, 3), ch)            # the legal END still works
+            assert sims.read_state(0)["grid"].sum() == 0
+
+    # a checkpoint only continues under the random stream it was saved with
+    opt = dict(n_replicas=3, n_events=500, order="fast", rng="philox", rng_seed=17)
+    with Replicas(Opt(**opt)) as a:
+        a.run(100)
+        blob = a.checkpoint()
+    for other in (dict(rng_seed=18), dict(first_replica=3)):
+        with Replicas(Opt(**{**opt, **other})) as b, pytest.raises(DcaError):
+            b.restore(blob)
+    with Replicas(Opt(n_events=500, order="fast", rng="mt19937", rng_seed=0)) as a:
+        a.run(100)
+        blob = a.checkpoint()
+    with Replicas(Opt(n_events=500, order="fast", rng="mt19937", rng_seed=1)) as b, pytest.raises(DcaError):
+        b.restore(blob)  # other tape
+    with Replicas(Opt(n_events=500, order="fast", rng="mt19937", rng_seed=0)) as b:
+        b.restore(blob)
+        b.run(400)
+        assert b.read_status(0)[:2] == (po.SUCCESS, 500)
+
+    # more END events than the queue has slots (only reachable through a forced grid): a status word, not a crash
+    for order in ("fast", "ref"):
+        with Replicas(Opt(n_replicas=2, n_events=20000, order=order, call_rate=3000.0, call_dur=1e7)) as sims:
+            for _ in range(4):  # every erase leaves the END events of the erased calls in the queue
+                sims.run(2500)
+                if sims.read_summary()["status"][1] != _ffi.RUNNING:
+                    break
+                assert sims.read_state(1)["grid"].sum() > 200
+                sims.write_state(1, grid=np.zeros((7, 7, 70), np.uint8))
+            s = sims.read_summary()
+            assert s["status"][0] == _ffi.RUNNING and s["status"][1] == _ffi.QUEUE_OVERFLOW, s["status"]
+            assert sims.sum_stats()[0][9] == 1
