@@ -834,6 +834,7 @@ int orc_eg_sizes(const orc_eventgen *eg, int *heap_n, int *events_n, int *endids
   return 0;
 }
 uint64_t orc_eg_ndraws(const orc_eventgen *eg) { return orc_rng_ndraws(eg->rng); }
+orc_rng *orc_eg_rng(orc_eventgen *eg) { return eg->rng; }
 
 /* ------------------------------------------------------------------------ */
 /* Simulator: src/Simulator.hs:59-134, src/SimRunner.hs:60-178              */

@@ -188,6 +188,7 @@ int orc_eg_generate_hoff_end(orc_eventgen *eg, double time, int r, int c, int ch
 int64_t orc_eg_id(const orc_eventgen *eg);
 int orc_eg_sizes(const orc_eventgen *eg, int *heap_n, int *events_n, int *endids_n);
 uint64_t orc_eg_ndraws(const orc_eventgen *eg);
+orc_rng *orc_eg_rng(orc_eventgen *eg);                          /* egGen */
 
 /* ---- simulator: src/Simulator.hs:59-134, src/SimRunner.hs:60-178 ---- */
 typedef struct orc_sim orc_sim;
@@ -216,6 +217,19 @@ int64_t orc_run_replicas(const orc_opt *base, int64_t first_replica, int n_repli
                          int64_t n_events, int n_threads, int64_t stats_sum8[8],
                          float *avg_reward_out, double *bp_out);
 int orc_max_threads(void);
+
+/* ---- the optimised CPU competitor (dca_cpu_fast.c): same path, FAST order, delta-form q-values, bit-mask
+ * grid, AVX2 over the rows of a feature plane, OpenMP over replicas.  Bit-exact against ORC_ORDER_FAST of
+ * the literal oracle above (tests/test_oracle_cpu_fast.py); bench.py's cpu_baseline times it. ---- */
+typedef struct cpf_sim cpf_sim;
+cpf_sim *cpf_create(const orc_opt *opt);
+void cpf_destroy(cpf_sim *s);
+int cpf_run(cpf_sim *s, int64_t max_steps, orc_trace *trace, int64_t trace_cap, int64_t *steps_done);
+void cpf_read(const cpf_sim *s, uint8_t *grid, int64_t *frep, float *w, float *wg, float *avg_reward,
+              int64_t *iter, orc_event *next_event, int64_t stats8[8]);
+uint64_t cpf_ndraws(const cpf_sim *s);
+int64_t cpf_run_replicas(const orc_opt *base, int64_t first_replica, int n_replicas, int64_t n_events,
+                         int n_threads, int64_t stats_sum8[8], float *avg_reward_out, double *bp_out);
 
 #ifdef __cplusplus
 }

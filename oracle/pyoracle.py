@@ -25,12 +25,11 @@ RUNNING, SUCCESS, ZERO_LOSS, NAN_LOSS, REUSE_VIOLATED, NELIG_OVERFLOW, HOST_ERRO
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc only, no reference sources)."""
-    src = os.path.join(_HERE, "dca_oracle.c")
-    hdr = os.path.join(_HERE, "dca_oracle.h")
+    srcs = [os.path.join(_HERE, f) for f in ("dca_oracle.c", "dca_cpu_fast.c", "dca_oracle.h", "Makefile")]
     stale = (
         force
         or not os.path.exists(_LIB_PATH)
-        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))
+        or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)
     )
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
@@ -155,6 +154,12 @@ def lib():
             "orc_stats_cumus": (None, [vp, vp]),
             "orc_run_replicas": (i64, [C.POINTER(Opt), i64, i32, i64, i32, vp, vp, vp]),
             "orc_max_threads": (i32, []),
+            "cpf_create": (vp, [C.POINTER(Opt)]),
+            "cpf_destroy": (None, [vp]),
+            "cpf_run": (i32, [vp, i64, vp, i64, vp]),
+            "cpf_read": (None, [vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+            "cpf_ndraws": (u64, [vp]),
+            "cpf_run_replicas": (i64, [C.POINTER(Opt), i64, i32, i64, i32, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -482,6 +487,54 @@ class Sim:
     @property
     def ndraws(self):
         return int(lib().orc_sim_ndraws(self.h))
+
+
+class FastSim(Sim):
+    """The optimised CPU competitor (oracle/dca_cpu_fast.c): FAST order, delta-form q-values, AVX2, same results
+    as Sim(order=ORDER_FAST) bit for bit."""
+
+    def __init__(self, opt: Opt | None = None, **kw):
+        self.opt = opt or default_opt(**kw)
+        self.opt.order = ORDER_FAST
+        self.h = lib().cpf_create(C.byref(self.opt))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().cpf_destroy(self.h)
+            self.h = None
+
+    def run(self, max_steps, trace=False):
+        tr = np.zeros(max_steps if trace else 0, dtype=TRACE_DTYPE)
+        done = C.c_int64()
+        status = lib().cpf_run(self.h, max_steps, _p(tr) if trace else None, len(tr), C.byref(done))
+        return status, done.value, (tr[: done.value] if trace else None)
+
+    def read(self):
+        grid = np.zeros((ROWS, COLS, CHANNELS), dtype=np.uint8)
+        frep = np.zeros((ROWS, COLS, NFEATS), dtype=np.int64)
+        w = np.zeros(FREP_SIZE, dtype=np.float32)
+        wg = np.zeros(FREP_SIZE, dtype=np.float32)
+        avg, it, ev = C.c_float(), C.c_int64(), Event()
+        stats = np.zeros(8, dtype=np.int64)
+        lib().cpf_read(self.h, _p(grid), _p(frep), _p(w), _p(wg), C.byref(avg), C.byref(it), C.byref(ev), _p(stats))
+        return dict(grid=grid, frep=frep, w=w, wg=wg, avg_reward=np.float32(avg.value), iter=it.value,
+                    event=ev.astuple(), stats=stats)
+
+    def period(self, reset=True):
+        raise NotImplementedError
+
+    @property
+    def ndraws(self):
+        return int(lib().cpf_ndraws(self.h))
+
+
+def run_replicas_fast(opt: Opt, first_replica, n_replicas, n_events, n_threads=0):
+    """OpenMP batch of the optimised CPU competitor; same return value as run_replicas."""
+    stats = np.zeros(8, dtype=np.int64)
+    avg = np.zeros(n_replicas, dtype=np.float32)
+    bp = np.zeros(n_replicas, dtype=np.float64)
+    total = lib().cpf_run_replicas(C.byref(opt), first_replica, n_replicas, n_events, n_threads, _p(stats), _p(avg), _p(bp))
+    return int(total), stats, avg, bp
 
 
 def grid_hash(grid) -> int:

@@ -1,0 +1,7 @@
+set -x
+cd $GRAFT_REPO_ROOT
+nvidia-smi -L
+nproc
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 300 python tools/step_cost.py > gpurun_out/r2_step_cost.json 2> gpurun_out/r2_step_cost.err; tail -3 gpurun_out/r2_step_cost.err; cat gpurun_out/r2_step_cost.json
+timeout 600 python bench.py > gpurun_out/r2_bench_v9b.json 2> gpurun_out/r2_bench_v9b.err; tail -3 gpurun_out/r2_bench_v9b.err; cat gpurun_out/r2_bench_v9b.json
