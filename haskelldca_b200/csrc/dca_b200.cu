@@ -1205,9 +1205,9 @@ extern "C" int dca_debug_cta(unsigned long long* out, int n_blocks) {
   return cudaMemcpyFromSymbol(out, dca::fast::g_cta, sizeof(unsigned long long) * 2 * (size_t)n_blocks) == cudaSuccess ? 0 : -1;
 }
 extern "C" int dca_debug_phase(unsigned long long* out, int reset) {
-  if (cudaMemcpyFromSymbol(out, dca::fast::g_phase, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(out, dca::fast::g_phase, sizeof(unsigned long long) * 48) != cudaSuccess) return -1;
   if (reset) {
-    unsigned long long z[32] = {0};
+    unsigned long long z[48] = {0};
     cudaMemcpyToSymbol(dca::fast::g_phase, z, sizeof z);
   }
   return 0;

@@ -50,6 +50,9 @@ constexpr int QCAPS = NBLK * 32;  // 704 >= QCAP: whole blocks can be scanned
 static_assert(QCAPS >= QCAP, "queue blocks");
 
 // Where wGradCorr lives (see struct Agent) and, with it, how many CTAs share an SM.
+#ifndef DCA_NO_END_SLOT_INDEX
+#define DCA_END_SLOT_INDEX
+#endif
 #if !defined(DCA_WG_REGS) && !defined(DCA_WG_TMEM)
 #define DCA_WG_TMEM  // measured on B200: 294.4 vs 287.9 M events/s (4096 replicas), 299.6 vs 292.1 M (5920)
 #endif
@@ -81,11 +84,12 @@ struct alignas(16) SmemF {
   uint32_t q_id[QCAPS];
   uint16_t q_key[QCAP];
   uint8_t q_hoff[QCAP];
-  double bm_t[NBLK];        // per block of 32 slots: its minimum (time, id) and where it is
-  uint32_t bm_id[NBLK];
-  uint16_t bm_s[NBLK];
-  uint16_t end_slot[NCELL][72];  // (cell, ch) -> slot of the END event of the call on ch at cell
-  Ev ev[2];
+#ifdef DCA_END_SLOT_INDEX
+  uint16_t end_slot[NCELL][72];  // (cell, ch) -> slot of the END event of the call on ch at cell (7 KB; without it
+                                 // reassign finds the slot by a warp-wide search of q_key and 6 CTAs fit an SM:
+                                 // measured 293 / 296 M events/s with 5 / 6 CTAs against 306 M with the index and 5)
+#endif
+  Ev ev[3];                 // the event warp runs ahead: it may fill record k + 2 while the agents still read record k
   float P[72];              // plane sums of x.w (current state, current weights)
   float q[72];              // afterstate values of the candidates
   float Wg[4];              // per-warp partial sums of x.wGradCorr
@@ -94,21 +98,39 @@ struct alignas(16) SmemF {
   uint32_t tmem_base;       // tensor-memory columns of this CTA (wGradCorr, DCA_WG_TMEM)
   float v_pub;              // V(s) of the current event, published by the agents before the argmax barrier
   uint32_t pad_[2];
+  uint2 n4rows[NCELL];      // per cell: byte r = the 7 column bits of row r of N4(cell) \ {cell} ...
+  uint2 n2rows[NCELL];      // ... and of N2(cell) u {cell}  (copied from the constant tables: a shared-memory load
+                            // with a computed index is ~5 x faster than a constant-memory one)
 };
+static_assert(sizeof(SmemF) <= (233472 / DCA_MIN_CTAS - 1024), "shared memory per CTA: DCA_MIN_CTAS of them must fit an SM");
 static_assert(sizeof(SmemF) % 16 == 0, "SmemF size");
 static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && offsetof(SmemF, grid) % 16 == 0 &&
               offsetof(SmemF, q_time) % 16 == 0 && offsetof(SmemF, q_id) % 16 == 0 && offsetof(SmemF, q_key) % 16 == 0 &&
-              offsetof(SmemF, q_hoff) % 8 == 0 && offsetof(SmemF, bm_t) % 8 == 0 && offsetof(SmemF, ev) % 8 == 0 &&
+              offsetof(SmemF, q_hoff) % 8 == 0 && offsetof(SmemF, ev) % 8 == 0 &&
               sizeof(Ev) % 8 == 0, "SmemF alignment");
 
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" ::: "memory"); }
-// named barrier 1, 96 threads (see agent_candidates): the event warp (next event published) and agent warp 2 (cnt2 moved to the
-// afterstate) arrive, agent warp 1 waits
-__device__ __forceinline__ void cand_signal() { asm volatile("bar.arrive 1, 96;" ::: "memory"); }
-__device__ __forceinline__ void cand_wait() { asm volatile("bar.sync 1, 96;" ::: "memory"); }
+// The per-event synchronisation of the run kernel is producer / consumer, so that neither side waits for the other
+// where it does not need its data:
+//   barrier 2 (96):  the agents among themselves -- every candidate's value is in sm.q
+//   barrier 3 (128): the same fact for the event warp: the agents arrive (and go on), the event warp waits
+//   barrier 4 (128): the next event's record (kind, cell, masks, candidates) and the stop status are published and the
+//                    plane sums of the dense pass are complete: the event warp arrives (and runs on to the next
+//                    event's queue work), the agents wait
+//   barrier 5 (128): TRACE instantiation only -- the afterstate is complete (the event warp hashes / verifies it)
+__device__ __forceinline__ void agents_q_ready() { asm volatile("bar.arrive 3, 128;\n\tbar.sync 2, 96;" ::: "memory"); }
+__device__ __forceinline__ void event_wait_q() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
+__device__ __forceinline__ void event_publish_next() { asm volatile("bar.arrive 4, 128;" ::: "memory"); }
+__device__ __forceinline__ void agents_wait_next() { asm volatile("bar.sync 4, 128;" ::: "memory"); }
+__device__ __forceinline__ void agents_afterstate_done() { asm volatile("bar.arrive 5, 128;" ::: "memory"); }
+__device__ __forceinline__ void event_wait_afterstate() { asm volatile("bar.sync 5, 128;" ::: "memory"); }
+// named barrier 1, 64 threads (see agent_candidates): agent warp 2 arrives once cnt2 is in its afterstate, the event warp
+// waits for that before it builds the next event's candidate list
+__device__ __forceinline__ void cand_signal() { asm volatile("bar.arrive 1, 64;" ::: "memory"); }
+__device__ __forceinline__ void cand_wait() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
 #ifdef DCA_PHASE_CLOCK  // development only: cycles per role (virtual warp) and phase, summed over CTAs and events
-__device__ unsigned long long g_phase[4][8];
+__device__ unsigned long long g_phase[6][8];  // rows 4, 5: sub-phases of the event warp's update phase
 __device__ unsigned long long g_cta[8192][2];  // per block: cycles in the run kernel, SM id
 #define DCA_CLK(v) const unsigned v = (unsigned)clock64()  /* 32-bit stamps and sums: few registers */
 // after a barrier: BAR.SYNC.DEFER_BLOCKING lets the warp run on to its first shared-memory access, so wait for one
@@ -119,7 +141,9 @@ __device__ unsigned long long g_cta[8192][2];  // per block: cycles in the run k
   }                                                            \
   const unsigned v = (unsigned)clock64()
 #define DCA_ACC(i, a, b) ph[i] += (b) - (a)
+#define DCA_SUB(i, a, b) sub[i] += (b) - (a)
 #else
+#define DCA_SUB(i, a, b)
 #define DCA_CLK(v)
 #define DCA_CLKB(v)
 #define DCA_ACC(i, a, b)
@@ -687,9 +711,10 @@ struct EvRegs {
   unsigned long long ndraws;
   long long iter, n_events, loss_n;
   float loss_sum, min_loss;
-  double mean_new, call_dur, call_dur_hoff, hoff_prob;
+  double mean_new, call_dur, call_dur_hoff;
+  unsigned long long hoff_thresh;       // p < hoffProb  <=>  (word >> 11) < ceil(hoffProb * 2^53)   (p = (word >> 11) * 2^-53 exactly)
   long long stats[8];                   // Stats counters (src/Stats.hs:15-30)
-  int dirty0, dirty1;                   // queue blocks whose minimum must be re-scanned (-1 = none)
+  int dirty1;                           // a second queue block whose minimum must be re-scanned after a pop (-1 = none; rare)
   unsigned long long dbase;             // cached draws: lane l holds draw dbase + l ...
   unsigned long long dword;             // ... its random word (per lane)
   double dnl;                           // ... and -log(u) of that word (per lane)
@@ -797,30 +822,26 @@ __device__ __forceinline__ void ev_candidates(const SmemF& sm, Ev& ev, const int
   __syncwarp();
 }
 
-// The run kernel splits that work.  The event warp is the longest dependency chain of the update phase
-// and the agent warps finish their dense pass well before it, so the event warp only publishes the next
-// event and the row masks of its cell (ev_masks) and signals named barrier 1; agent warp 1 waits there
-// after its dense pass and builds the candidate list (agent_candidates) -- by then cnt2 and the grid are
-// in their afterstate (agent warp 2 signals the same barrier after moving cnt2, the grid bit precedes the
-// event warp's signal), so no channel needs a special case.
-#ifndef DCA_CAND_WARP
-#define DCA_CAND_WARP 1
-#endif
-constexpr int CAND_WARP = DCA_CAND_WARP;  // the agent warp that builds the candidate list
-__device__ __forceinline__ void ev_masks(Ev& ev, const int cell) {
+// The run kernel splits that work: the event warp pops the next event while the agents still evaluate the current
+// one's candidates (the pop does not depend on the chosen channel) and publishes its kind, cell and row masks
+// (ev_masks); after the decision it sets the grid bit, waits at named barrier 1 until agent warp 2 has moved cnt2 to the
+// afterstate, and builds the candidate list (agent_candidates) -- grid and cnt2 are in their afterstate then, so no
+// channel needs a special case.
+// the row byte masks of the next event's cell, from the shared tables (part of the record the event warp publishes)
+__device__ __forceinline__ void ev_masks(const SmemF& sm, Ev& ev, const int cell) {
   const int lane = lane_id();
-  const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
   if (lane < 8) {
-    ev.n4b[lane] = (lane < 7) ? spread7((uint32_t)(n4 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
-    ev.n2b[lane] = (lane < 7) ? spread7((uint32_t)(n2 >> (7 * lane)) & 0x7Fu) : make_uint2(0, 0);
+    const uint2 a = sm.n4rows[cell], b = sm.n2rows[cell];
+    const int sh = 8 * (lane & 3);
+    const uint32_t r4 = ((lane < 4 ? a.x : a.y) >> sh) & 0x7Fu, r2 = ((lane < 4 ? b.x : b.y) >> sh) & 0x7Fu;  // (row 7: 0)
+    ev.n4b[lane] = spread7(r4);
+    ev.n2b[lane] = spread7(r2);
   }
 }
-__device__ __forceinline__ void agent_candidates(const SmemF& sm, Ev& ev) {
+__device__ __forceinline__ int agent_candidates(const SmemF& sm, Ev& ev, const int type, const int cell) {  // returns their number
   const int lane = lane_id();
-  const int2 tc = *reinterpret_cast<const int2*>(&ev.type);  // (type, cell): adjacent, 8-byte aligned -- one load
-  const int cell = tc.y;
   uint32_t m[3];
-  if (tc.x == EV_END) {     // inuseChs, Gridfuncs.hs:86-87
+  if (type == EV_END) {     // inuseChs, Gridfuncs.hs:86-87
     const uint4 g = *reinterpret_cast<const uint4*>(&sm.grid[cell][0]);
     m[0] = g.x; m[1] = g.y; m[2] = g.z;
   } else {                  // eligibleChs, Gridfuncs.hs:69-82  <=>  nobody within distance 2 (incl. the cell) uses ch
@@ -838,89 +859,74 @@ __device__ __forceinline__ void agent_candidates(const SmemF& sm, Ev& ev) {
     base += __popc(m[j]);
   }
   if (lane == 0) ev.ncand = base;
+  return base;
 }
 
 // ---- the event queue (EventGen, src/EventGen/Internal.hs:44-53) as a dense slot table with
 // per-block minima: pop = argmin over (time, id) (EventGen.hs:39-50) costs one 22-wide reduction
 // plus the re-scan of the one or two 32-slot blocks it touched.
-struct QMin {
-  unsigned long long t;
-  unsigned id, lane;
-};
-// lexicographic warp argmin over (t, id); every lane gets the result and the winning lane
-__device__ __forceinline__ QMin warp_argmin(unsigned long long t, unsigned id) {
+// lexicographic warp argmin over (t, id): the lane that holds the minimum (the first one among equals).  The upper
+// 32 bits of the time almost always decide (event times are spread over minutes, the upper word resolves ~1e-6 of
+// one): one reduction and a ballot; the lower word and the id follow only when two lanes tie (warp-uniform).
+__device__ __forceinline__ unsigned warp_argmin_lane(unsigned long long t, unsigned id) {
   const unsigned hi = (unsigned)(t >> 32), lo = (unsigned)t;
   const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
   bool ok = hi == mhi;
-  const unsigned mlo = __reduce_min_sync(0xffffffffu, ok ? lo : 0xFFFFFFFFu);
-  ok = ok && lo == mlo;
-  const unsigned mid = __reduce_min_sync(0xffffffffu, ok ? id : 0xFFFFFFFFu);
-  ok = ok && id == mid;
-  QMin m;
-  m.t = ((unsigned long long)mhi << 32) | mlo;
-  m.id = mid;
-  m.lane = __ffs(__ballot_sync(0xffffffffu, ok)) - 1;
-  return m;
-}
-__device__ __forceinline__ void q_block_rescan(SmemF& sm, unsigned b) {
-  const int lane = lane_id();
-  const unsigned i = 32 * b + lane;
-  const QMin m = warp_argmin((unsigned long long)__double_as_longlong(sm.q_time[i]), sm.q_id[i]);
-  if (lane == 0) {
-    sm.bm_t[b] = __longlong_as_double((long long)m.t);
-    sm.bm_id[b] = m.id;
-    sm.bm_s[b] = (uint16_t)(32 * b + m.lane);
+  unsigned eq = __ballot_sync(0xffffffffu, ok);
+  if (eq & (eq - 1)) {
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, ok ? lo : 0xFFFFFFFFu);
+    ok = ok && lo == mlo;
+    eq = __ballot_sync(0xffffffffu, ok);
+    if (eq & (eq - 1)) {
+      const unsigned mid = __reduce_min_sync(0xffffffffu, ok ? id : 0xFFFFFFFFu);
+      eq = __ballot_sync(0xffffffffu, ok && id == mid);
+    }
   }
+  return __ffs(eq) - 1;
 }
-// a slot was just written with (t, id): lower its block's minimum if needed
-__device__ __forceinline__ void q_block_push(SmemF& sm, unsigned slot, unsigned long long t, unsigned id) {
-  __syncwarp();  // (an earlier push of this event may have lowered the same block)
-  const unsigned b = slot >> 5;
-  const unsigned long long bt = (unsigned long long)__double_as_longlong(sm.bm_t[b]);
-  const unsigned bid = sm.bm_id[b];
-  if (lane_id() == 0 && (t < bt || (t == bt && id < bid))) {
-    sm.bm_t[b] = __longlong_as_double((long long)t);
-    sm.bm_id[b] = id;
-    sm.bm_s[b] = (uint16_t)slot;
-  }
+// The minimum (time, id) of every block of 32 slots and where it is: lane b of the event warp keeps block b's in
+// REGISTERS (lanes >= NBLK: +inf).  The event warp's chain is bound by shared-memory round trips -- under the agents'
+// load one costs ~100 cycles -- so the per-block minima never go through shared memory.
+struct QBlk {
+  unsigned long long t;
+  unsigned id, s;
+};
+__device__ __forceinline__ void q_block_rescan(const SmemF& sm, QBlk& qb, const unsigned b) {
+  const unsigned i = 32 * b + lane_id();
+  const unsigned long long t = (unsigned long long)__double_as_longlong(sm.q_time[i]);
+  const unsigned id = sm.q_id[i];
+  const unsigned w = warp_argmin_lane(t, id);
+  const unsigned long long tw = __shfl_sync(0xffffffffu, t, (int)w);
+  const unsigned idw = __shfl_sync(0xffffffffu, id, (int)w);
+  if ((unsigned)lane_id() == b) { qb.t = tw; qb.id = idw; qb.s = 32 * b + w; }
+}
+// a slot of block b was just written with (t, id): lower the block's minimum if needed (lane-local)
+__device__ __forceinline__ void q_block_lower(QBlk& qb, const unsigned b, const unsigned slot, const unsigned long long t,
+                                              const unsigned id) {
+  if ((unsigned)lane_id() == b && (t < qb.t || (t == qb.t && id < qb.id))) { qb.t = t; qb.id = id; qb.s = slot; }
 }
 // slot of the earliest stored event
-__device__ __forceinline__ unsigned q_min_slot(const SmemF& sm) {
-  const int lane = lane_id();
-  unsigned long long t = 0xFFFFFFFFFFFFFFFFULL;
-  unsigned id = 0xFFFFFFFFu;
-  if (lane < NBLK) {
-    t = (unsigned long long)__double_as_longlong(sm.bm_t[lane]);
-    id = sm.bm_id[lane];
-  }
-  const QMin m = warp_argmin(t, id);
-  return sm.bm_s[m.lane];
+__device__ __forceinline__ unsigned q_min_slot(const QBlk& qb) {
+  const unsigned w = warp_argmin_lane(qb.t, qb.id);
+  return __shfl_sync(0xffffffffu, qb.s, (int)w);
 }
 // everything derived from the slot table (run once per launch by the event warp)
-__device__ __forceinline__ void q_build(SmemF& sm, unsigned n_end) {
+__device__ __forceinline__ void q_build(SmemF& sm, QBlk& qb, unsigned n_end) {
   const int lane = lane_id();
   for (unsigned i = QNEW + n_end + lane; i < QCAPS; i += 32) {  // unused slots never win
     sm.q_time[i] = CUDART_INF;
     sm.q_id[i] = 0xFFFFFFFFu;
   }
+#ifdef DCA_END_SLOT_INDEX
   for (unsigned i = QNEW + lane; i < QNEW + n_end; i += 32) {
     const unsigned key = sm.q_key[i];
     sm.end_slot[key >> 7][key & 127u] = (uint16_t)i;
   }
+#endif
   __syncwarp();
+  qb.t = 0xFFFFFFFFFFFFFFFFULL; qb.id = 0xFFFFFFFFu; qb.s = 0;
 #pragma unroll 1
-  for (unsigned b = 0; b < NBLK; ++b) q_block_rescan(sm, b);
-  __syncwarp();
-}
-
-// what the event warp does while the agents evaluate the candidates of `ev`: re-scan the queue
-// blocks the last pop touched (their minima are needed by the next push / pop) and make sure the
-// random draws of this event are cached
-__device__ __forceinline__ void ev_prepare(SmemF& sm, EvRegs& e, const Ev& ev) {
-  if (e.dirty0 >= 0) q_block_rescan(sm, (unsigned)e.dirty0);
-  if (e.dirty1 >= 0) q_block_rescan(sm, (unsigned)e.dirty1);
-  e.dirty0 = e.dirty1 = -1;
-  if (ev.type != EV_END) ev_draws(e);
+  for (unsigned b = 0; b < NBLK; ++b) q_block_rescan(sm, qb, b);
   __syncwarp();
 }
 
@@ -936,7 +942,7 @@ struct EnvNext {                 // the next event (registers, warp-uniform)
 };
 
 // part 1: statistics and the new events (EventGen.hs:75-116)
-__device__ __forceinline__ int ev_env_push(SmemF& sm, EvRegs& e, const int type, const int cell, const double time,
+__device__ __forceinline__ int ev_env_push(SmemF& sm, EvRegs& e, QBlk& qb, const int type, const int cell, const double time,
                                            const bool accepted) {
   const int lane = lane_id();
   int pend_slot = -1;
@@ -951,23 +957,21 @@ __device__ __forceinline__ int ev_env_push(SmemF& sm, EvRegs& e, const int type,
   } else {
     e.stats[4]++;
   }
-  bool have_end = false;
-  unsigned long long t_end = 0;
-  unsigned id_end = 0;
+  bool have_end = false, have_new = false;
+  unsigned long long t_end = 0, t_new = 0;
+  unsigned id_end = 0, id_new = 0;
   int end_hoff = HOFF_NONE;
   if (type == EV_NEW) {
     // generateNewEvent, EventGen.hs:75-85: always, at time + Exp(mean_new)
-    const double tn = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 0), e.mean_new));
-    const unsigned id_new = e.next_id++;
-    if (lane == 0) { sm.q_time[cell] = tn; sm.q_id[cell] = id_new; }
-    q_block_push(sm, (unsigned)cell, (unsigned long long)__double_as_longlong(tn), id_new);
+    t_new = (unsigned long long)__double_as_longlong(__dadd_rn(time, __dmul_rn(ev_draw_nl(e, 0), e.mean_new)));
+    id_new = e.next_id++;
+    have_new = true;
     unsigned used = 1;
     if (accepted) {
-      const unsigned long long w1 = ev_draw_word(e, 1);
-      const double p = __dmul_rn((double)(w1 >> 11), 1.0 / 9007199254740992.0);  // Simulator.hs:121
+      const unsigned long long w1 = ev_draw_word(e, 1);  // p = stdUniform, Simulator.hs:121
       const double te = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 2), e.call_dur));  // callDurNew for both kinds, EventGen.hs:102,112
       used = 3;
-      if (p < e.hoff_prob) {  // generateHoffNewEvent, EventGen.hs:94-109
+      if ((w1 >> 11) < e.hoff_thresh) {  // p < hoffProb: generateHoffNewEvent, EventGen.hs:94-109
         const int m = c_tab.n2cnt[cell];
         const int n_reject = 256 % m;
         int z;
@@ -995,31 +999,46 @@ __device__ __forceinline__ int ev_env_push(SmemF& sm, EvRegs& e, const int type,
       e.ndraws += 1;
     }
   }
-  if (have_end) {  // push END (cell, <channel pending>) [hoff] at slot QNEW + n_end
-    const unsigned slot = QNEW + e.n_end;
-    if (slot < QCAP) {
-      if (lane == 0) {
-        sm.q_time[slot] = __longlong_as_double((long long)t_end);
-        sm.q_id[slot] = id_end;
-        sm.q_key[slot] = (uint16_t)((cell << 7) | CH_PENDING);
-        sm.q_hoff[slot] = (uint8_t)end_hoff;
-      }
-      q_block_push(sm, slot, t_end, id_end);
-      pend_slot = (int)slot;
+  // the queue writes: NEW at slot `cell`, END (cell, <channel pending>) [hoff] at slot QNEW + n_end -- by lane 0 (the only
+  // thread that ever writes the slot table); the minima of the blocks they fall into are lowered in their lanes' registers
+  const unsigned slot_end = QNEW + e.n_end;
+  if (have_end) {
+    if (slot_end < QCAP) {
+      pend_slot = (int)slot_end;
       e.n_end++;
     } else {
       // the table is full (more than QEND calls in progress: impossible while the reuse constraint holds, reachable
       // only from a grid forced in through dca_write_state): nothing is written, n_end stays in bounds, and the
       // caller stops the replica with ST_QUEUE_OVERFLOW
       pend_slot = PEND_OVERFLOW;
+      have_end = false;
     }
+  }
+  if (have_new) {
+    if (lane == 0) {
+      sm.q_time[cell] = __longlong_as_double((long long)t_new);
+      sm.q_id[cell] = id_new;
+    }
+    q_block_lower(qb, (unsigned)cell >> 5, (unsigned)cell, t_new, id_new);
+  }
+  if (have_end) {
+    if (lane == 0) {
+      sm.q_time[slot_end] = __longlong_as_double((long long)t_end);
+      sm.q_id[slot_end] = id_end;
+      sm.q_key[slot_end] = (uint16_t)((cell << 7) | CH_PENDING);
+      sm.q_hoff[slot_end] = (uint8_t)end_hoff;
+    }
+    q_block_lower(qb, slot_end >> 5, slot_end, t_end, id_end);
   }
   __syncwarp();
   return pend_slot;
 }
 
-// part 2: the next event (Simulator.hs:132-134)
-__device__ __forceinline__ EnvNext ev_env_pop(SmemF& sm, EvRegs& e, const int type, const int ev_hoff,
+// part 2: the next event (Simulator.hs:132-134).  The pop and the re-scan of the block it empties are ONE shared-memory
+// round trip: the popped entry, its whole block and (up front, while the argmin runs) the last END entry -- which moves
+// into the hole to keep the table dense -- are loaded together, the lanes whose slots change substitute the new values
+// in registers, and the block's new minimum is reduced from those.
+__device__ __forceinline__ EnvNext ev_env_pop(SmemF& sm, EvRegs& e, QBlk& qb, const int type, const int ev_hoff,
                                               const double time, const int pend_slot) {
   const int lane = lane_id();
   EnvNext nx;
@@ -1030,46 +1049,83 @@ __device__ __forceinline__ EnvNext ev_env_pop(SmemF& sm, EvRegs& e, const int ty
     // the HOFF that follows a hand-off END: same time, next id (EventGen.hs:107-108)
     nx.time = time; nx.type = EV_HOFF; nx.cell = ev_hoff;
   } else {  // pop, EventGen.hs:39-50
-    const unsigned slot = q_min_slot(sm);
+    const unsigned last = QNEW + e.n_end - 1;  // (no END event stored: slot QNEW - 1, a harmless load)
+    const unsigned long long lt = (unsigned long long)__double_as_longlong(sm.q_time[last]);
+    const unsigned lid = sm.q_id[last], lkey = sm.q_key[last], lhoff = sm.q_hoff[last];
+    const unsigned slot = q_min_slot(qb);
+    const unsigned b = slot >> 5, i = 32 * b + (unsigned)lane;
     nx.time = sm.q_time[slot];
+    const int key = sm.q_key[slot < (unsigned)QCAP ? slot : 0];
+    const int hoff = sm.q_hoff[slot < (unsigned)QCAP ? slot : 0];
+    unsigned long long bt = (unsigned long long)__double_as_longlong(sm.q_time[i]);
+    unsigned bid = sm.q_id[i];
     if (slot < QNEW) {
       nx.type = EV_NEW; nx.cell = (int)slot;
-      __syncwarp();
       if (lane == 0) { sm.q_time[slot] = CUDART_INF; sm.q_id[slot] = 0xFFFFFFFFu; }
-      e.dirty0 = (int)(slot >> 5);
+      if (i == slot) { bt = 0x7FF0000000000000ULL; bid = 0xFFFFFFFFu; }
     } else {
-      const int key = sm.q_key[slot];
-      nx.type = EV_END; nx.cell = key >> 7; nx.ch = key & 127; nx.hoff = sm.q_hoff[slot];
-      const unsigned last = QNEW + e.n_end - 1;
-      const bool last_was_min = sm.bm_s[last >> 5] == last;
-      __syncwarp();
+      nx.type = EV_END; nx.cell = key >> 7; nx.ch = key & 127; nx.hoff = hoff;
+      const bool last_was_min = __shfl_sync(0xffffffffu, qb.s, (int)(last >> 5)) == last;
       if (lane == 0) {
         if (slot != last) {  // keep the table dense: the last END event moves into the hole
-          const unsigned lkey = sm.q_key[last];
-          sm.q_time[slot] = sm.q_time[last];
-          sm.q_id[slot] = sm.q_id[last];
+          sm.q_time[slot] = __longlong_as_double((long long)lt);
+          sm.q_id[slot] = lid;
           sm.q_key[slot] = (uint16_t)lkey;
-          sm.q_hoff[slot] = sm.q_hoff[last];
+          sm.q_hoff[slot] = (uint8_t)lhoff;
+#ifdef DCA_END_SLOT_INDEX
           if ((lkey & 127u) != CH_PENDING) sm.end_slot[lkey >> 7][lkey & 127u] = (uint16_t)slot;
+#endif
         }
         sm.q_time[last] = CUDART_INF;
         sm.q_id[last] = 0xFFFFFFFFu;
       }
+      if (i == slot) { bt = lt; bid = lid; }                                  // the hole takes the last entry ...
+      if (i == last) { bt = 0x7FF0000000000000ULL; bid = 0xFFFFFFFFu; }      // ... whose own slot is empty now
       if ((int)slot == nx.pend_slot) nx.pend_slot = -1;         // the END just pushed is the next event: not stored
       else if ((int)last == nx.pend_slot) nx.pend_slot = (int)slot;  // ... or it moved into the hole
       e.n_end--;
-      e.dirty0 = (int)(slot >> 5);
-      if ((last >> 5) != (slot >> 5) && last_was_min) e.dirty1 = (int)(last >> 5);
+      if ((last >> 5) != b && last_was_min) e.dirty1 = (int)(last >> 5);
     }
+    // the new minimum of the block the pop touched
+    const unsigned w = warp_argmin_lane(bt, bid);
+    const unsigned long long tw = __shfl_sync(0xffffffffu, bt, (int)w);
+    const unsigned idw = __shfl_sync(0xffffffffu, bid, (int)w);
+    if ((unsigned)lane == b) { qb.t = tw; qb.id = idw; qb.s = 32 * b + w; }
   }
   __syncwarp();
   return nx;
 }
 
+// slot of the END event with key `key` among the n_end stored ones (reassign, EventGen.hs:62-72): warp-wide search of
+// q_key, eight keys per 16-byte load.  Slots past the live range may hold stale copies of live keys: only indices
+// below QNEW + n_end count; a live key is unique.  (NEW slots carry channel 127 and never match.)
+__device__ __forceinline__ unsigned q_find_end(const SmemF& sm, const unsigned key, const unsigned n_end) {
+  const unsigned lane = (unsigned)lane_id();
+  const unsigned limit = QNEW + n_end;
+  const unsigned want2 = key * 0x00010001u;
+  unsigned found = 0xFFFFFFFFu;
+#pragma unroll
+  for (unsigned r = 0; r < 3; ++r) {
+    const unsigned v = lane + 32u * r;
+    if (v < (unsigned)QCAP / 8u) {
+      const uint4 k = reinterpret_cast<const uint4*>(sm.q_key)[v];
+      const unsigned w[4] = {k.x, k.y, k.z, k.w};
+#pragma unroll
+      for (unsigned j = 0; j < 4; ++j) {
+        const unsigned m = __vcmpeq2(w[j], want2);
+        const unsigned i0 = 8u * v + 2u * j;
+        if ((m & 0xFFFFu) && i0 < limit) found = min(found, i0);
+        if ((m >> 16) && i0 + 1u < limit) found = min(found, i0 + 1u);
+      }
+    }
+  }
+  return __reduce_min_sync(0xffffffffu, found);
+}
+
 // the channel-dependent rest, once `act` (-1 = Nothing) is known; writes the next event to `out`
 template <bool GRID_BIT = true>
 __device__ __forceinline__ void ev_env_post(SmemF& sm, Ev& out, EnvNext nx, const int type, const int cell,
-                                            const int ev_ch, const int act) {
+                                            const int ev_ch, const int act, const unsigned n_end) {
   const int lane = lane_id();
   if (nx.ch == CH_PENDING) nx.ch = act;  // the call accepted just now ends before anything else happens
   bool rekey = false;
@@ -1079,18 +1135,30 @@ __device__ __forceinline__ void ev_env_post(SmemF& sm, Ev& out, EnvNext nx, cons
     if (nx.type == EV_END && nx.cell == cell && nx.ch == act) nx.ch = ev_ch;
     else rekey = true;
   }
+#ifdef DCA_END_SLOT_INDEX
+  (void)n_end;
+  unsigned rekey_slot = 0;
+#else
+  unsigned rekey_slot = 0;
+  if (rekey) rekey_slot = q_find_end(sm, (unsigned)((cell << 7) | act), n_end);  // warp-uniform
+#endif
   if (lane == 0) {
     if (GRID_BIT && act >= 0) sm.grid[cell][act >> 5] ^= 1u << (act & 31);  // executeAction, Gridfuncs.hs:105-110
     if (nx.pend_slot >= 0) {
       sm.q_key[nx.pend_slot] = (uint16_t)((cell << 7) | act);
+#ifdef DCA_END_SLOT_INDEX
       sm.end_slot[cell][act] = (uint16_t)nx.pend_slot;
+#endif
     }
     if (rekey) {
-      const unsigned sl = sm.end_slot[cell][act];
-      sm.q_key[sl] = (uint16_t)((cell << 7) | ev_ch);
-      sm.end_slot[cell][ev_ch] = (uint16_t)sl;
+#ifdef DCA_END_SLOT_INDEX
+      rekey_slot = sm.end_slot[cell][act];
+      sm.end_slot[cell][ev_ch] = (uint16_t)rekey_slot;
+#endif
+      if (rekey_slot < (unsigned)QCAP) sm.q_key[rekey_slot] = (uint16_t)((cell << 7) | ev_ch);
     }
-    out.time = nx.time; out.type = nx.type; out.cell = nx.cell; out.ch = nx.ch; out.hoff = nx.hoff;
+    out.time = nx.time; out.ch = nx.ch; out.hoff = nx.hoff;
+    if (GRID_BIT) { out.type = nx.type; out.cell = nx.cell; }  // (the run kernel publishes kind and cell right after the pop)
   }
   __syncwarp();
 }
@@ -1179,7 +1247,18 @@ __device__ __forceinline__ void stage_in(SmemF& sm, const RepState* g) {
   copy16(sm.q_id, g->q_id, sizeof g->q_id);
   copy16(sm.q_key, g->q_key, sizeof sm.q_key);
   copy8(sm.q_hoff, g->q_hoff, sizeof sm.q_hoff);
-  if (threadIdx.x < 72) sm.ev[0].cand[threadIdx.x] = sm.ev[1].cand[threadIdx.x] = 0;  // (read before ncand is known)
+  if (threadIdx.x < 72) sm.ev[0].cand[threadIdx.x] = sm.ev[1].cand[threadIdx.x] = sm.ev[2].cand[threadIdx.x] = 0;  // (read before ncand is known)
+  if (threadIdx.x < NCELL) {
+    const unsigned long long n4 = c_tab.n4excl[threadIdx.x], n2 = c_tab.n2incl[threadIdx.x];
+    unsigned long long r4 = 0, r2 = 0;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      r4 |= ((n4 >> (7 * r)) & 0x7FULL) << (8 * r);
+      r2 |= ((n2 >> (7 * r)) & 0x7FULL) << (8 * r);
+    }
+    sm.n4rows[threadIdx.x] = make_uint2((uint32_t)r4, (uint32_t)(r4 >> 32));
+    sm.n2rows[threadIdx.x] = make_uint2((uint32_t)r2, (uint32_t)(r2 >> 32));
+  }
   if (threadIdx.x == 0) {
     sm.P[NCH + 1] = 0.0f;  // the pad leaf of the V tree
     Ev& ev = sm.ev[0];
@@ -1241,10 +1320,14 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
   e.n_end = g->n_end; e.next_id = g->next_id; e.ndraws = g->ndraws;
   e.iter = g->iter; e.n_events = g->n_events; e.loss_n = g->loss_n;
   e.loss_sum = g->loss_sum; e.min_loss = g->min_loss;
-  e.mean_new = g->mean_new; e.call_dur = g->call_dur; e.call_dur_hoff = g->call_dur_hoff; e.hoff_prob = g->hoff_prob;
+  e.mean_new = g->mean_new; e.call_dur = g->call_dur; e.call_dur_hoff = g->call_dur_hoff;
+  {  // hoffProb as an integer threshold on the 53 random bits (exact: scaling by 2^53 and ceil are)
+    const double h = g->hoff_prob;
+    e.hoff_thresh = !(h > 0.0) ? 0ULL : (h >= 1.0 ? (1ULL << 53) : (unsigned long long)ceil(h * 9007199254740992.0));
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) e.stats[k] = g->stats[k];
-  e.dirty0 = e.dirty1 = -1;
+  e.dirty1 = -1;
   e.dbase = 0xFFFFFFFFFFFFFFF0ULL; e.dword = 0; e.dnl = 0.0;  // (empty draw cache)
   e.rng_mode = a.rng_mode; e.k0 = a.key0; e.k1 = a.key1; e.stream = g->stream;
   e.tape_w = nullptr; e.tape_l = nullptr; e.tape_len = 0;
@@ -1278,10 +1361,12 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
 #ifdef DCA_PHASE_CLOCK
   unsigned ph[6] = {0, 0, 0, 0, 0, 0};
 #endif
+  int cur = 0;  // index of the current event's record (it % 3)
 #pragma unroll 1
   for (long long it = 0; it < a.max_events; ++it) {
     DCA_CLK(c0);
-    const Ev& ev = sm.ev[it & 1];
+    const Ev& ev = sm.ev[cur];
+    cur = cur == 2 ? 0 : cur + 1;
     const int n = ev.ncand;
     const bool is_end = ev.type == EV_END;
     const uint2 n4b_r = ev.n4b[rc], n2b_r = ev.n2b[rc];
@@ -1291,19 +1376,15 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
     if (l.vw == 0 && lane_id() == 0) sm.v_pub = vt.val;
     DCA_CLK(c1);
-    cta_barrier();  // B2
+    agents_q_ready();  // B2
     DCA_CLKB(c2);
     const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
     dense_pass<true, true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
-    if (l.vw == CAND_WARP) {  // warp-uniform: the next event's candidate channels (getAction, Simulator.hs:161-165)
-      cand_wait();
-      agent_candidates(sm, sm.ev[(it & 1) ^ 1]);
-    }
     DCA_CLK(c4);
-    if (sync_end) cta_barrier();
-    cta_barrier();  // B1
+    if (sync_end) agents_afterstate_done();
+    agents_wait_next();  // B1
     DCA_CLKB(c5);
     DCA_ACC(0, c0, c1); DCA_ACC(1, c1, c2); DCA_ACC(2, c2, c3); DCA_ACC(3, c3, c4); DCA_ACC(4, c4, c5); DCA_ACC(5, c0, c5);
     if (sm.status != ST_RUNNING) break;  // uniform
@@ -1331,17 +1412,33 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   EvRegs e;
   ev_load(e, a, g, rep);
   cta_barrier();
-  q_build(sm, e.n_end);
+  QBlk qb;
+  q_build(sm, qb, e.n_end);
   ev_candidates(sm, sm.ev[0], -1);
+  // The event warp runs one step AHEAD of the agents: the new events of an event (ev_env_push needs only whether it
+  // has a candidate) are pushed at the end of the previous event's update phase, its successor is popped while the
+  // agents evaluate its candidates.  pend_slot / q_overflow carry the result of the push to the event it belongs to.
+  int pend_slot = -1;
+  bool q_overflow = false;
+  if (a.max_events > 0) {
+    const Ev& ev0 = sm.ev[0];
+    if (ev0.type != EV_END) ev_draws(e);
+    const int pushed = ev_env_push(sm, e, qb, ev0.type, ev0.cell, ev0.time, ev0.ncand > 0);  // Simulator.hs:101-128
+    q_overflow = pushed == PEND_OVERFLOW;
+    pend_slot = q_overflow ? -1 : pushed;
+  }
   cta_barrier();  // B1
   long long it = 0;
 #ifdef DCA_PHASE_CLOCK
   unsigned ph[6] = {0, 0, 0, 0, 0, 0};
+  unsigned sub[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
+  int cur = 0;  // index of the current event's record (it % 3)
 #pragma unroll 1
   for (; it < a.max_events; ++it) {
-    const Ev& ev = sm.ev[it & 1];
-    Ev& nx = sm.ev[(it & 1) ^ 1];
+    const Ev& ev = sm.ev[cur];
+    cur = cur == 2 ? 0 : cur + 1;
+    Ev& nx = sm.ev[cur];
     const int type = ev.type, cell = ev.cell, n = ev.ncand;
     const int ev_ch = ev.ch, ev_hoff = ev.hoff;
     const double time = ev.time;
@@ -1350,11 +1447,14 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     // (this warp needs V(s) only for the TD error it logs and tests: the agents publish it; the TD scalars
     //  of the weight update are not needed here)
     const DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
-    ev_prepare(sm, e, ev);
+    // Ahead of the agents (they may still be in the previous event's dense pass): the pop of the next event -- it
+    // does not depend on WHICH channel is chosen, and this event's new events are in the queue already.  Its kind
+    // and cell go to the next event record (nobody reads that one before barrier 4).
+    const bool overflow_now = q_overflow;
+    const EnvNext en = ev_env_pop(sm, e, qb, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
+    if (lane == 0) { nx.type = en.type; nx.cell = en.cell; }
     DCA_CLK(c1);
-    // (ev_env_push / ev_env_pop do not depend on the chosen channel and could run before B2; measured on
-    //  B200 that makes this warp the late one at B2: 245 / 233 M events/s instead of 251 M)
-    cta_barrier();  // B2
+    event_wait_q();  // B2: the agents have evaluated the candidates
     DCA_CLKB(c2);
     VTree vt;
     vt.val = sm.v_pub;
@@ -1362,16 +1462,20 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
     DCA_CLK(c3);
     if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);  // executeAction, Gridfuncs.hs:105-110
-    const int pushed = ev_env_push(sm, e, type, cell, time, n > 0);         // Simulator.hs:101-128: new events
-    const bool q_overflow = pushed == PEND_OVERFLOW;
-    const int pend_slot = q_overflow ? -1 : pushed;
-    const EnvNext en = ev_env_pop(sm, e, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
-    // the candidate list of the next event needs its kind and cell, the grid and cnt2: all known here
-    if (lane == 0) { nx.type = en.type; nx.cell = en.cell; }
-    ev_masks(nx, en.cell);
-    __syncwarp();
-    cand_signal();  // agent warp 1 builds the candidate list
-    ev_env_post<false>(sm, nx, en, type, cell, ev_ch, d.act);                // the channel-dependent rest
+    ev_env_post<false>(sm, nx, en, type, cell, ev_ch, d.act, e.n_end);       // the channel-dependent rest
+    DCA_CLK(s0);
+    // the queue blocks the pop touched: their minima are needed by the next event's push / pop
+    if (e.dirty1 >= 0) q_block_rescan(sm, qb, (unsigned)e.dirty1);  // (rare: the entry moved into the hole was its block's minimum)
+    e.dirty1 = -1;
+    DCA_CLK(s1);
+    ev_masks(sm, nx, en.cell);
+    DCA_CLK(s2);
+    // the next event's candidate channels (getAction, Simulator.hs:161-165): the grid bit is set (above), cnt2 is in
+    // its afterstate once agent warp 2 has arrived at named barrier 1
+    cand_wait();
+    DCA_CLKB(s3);
+    const int n_next = agent_candidates(sm, nx, en.type, en.cell);
+    DCA_CLK(s4);
     e.iter += 1;  // Simulator.hs:131
     // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
     int stop = ST_RUNNING;
@@ -1380,9 +1484,9 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
       e.loss_sum = __fadd_rn(e.loss_sum, d.tderr);
       e.loss_n += 1;
     }
-    if (stop == ST_RUNNING && q_overflow) stop = ST_QUEUE_OVERFLOW;
+    if (stop == ST_RUNNING && overflow_now) stop = ST_QUEUE_OVERFLOW;
     if (sync_end) {
-      cta_barrier();  // the agents have moved frep to the afterstate
+      event_wait_afterstate();  // the agents have moved frep to the afterstate
       if (stop == ST_RUNNING && (a.verify_rc || a.verify_nb)) {
         const int v = ev_verify(sm, a.verify_rc, a.verify_nb);
         if (v) stop = v;
@@ -1411,20 +1515,30 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     if (stop == ST_RUNNING && e.iter == e.n_events) stop = ST_SUCCESS;
     if (stop == ST_RUNNING && e.rng_mode == RNG_TAPE && e.ndraws + 8 > e.tape_len) stop = ST_TAPE_EXHAUSTED;
     if (lane == 0) sm.status = stop;
+    DCA_CLK(s5);
+    event_publish_next();  // B1 (non-blocking): the next event's record and the status are published
+    if (stop == ST_RUNNING && it + 1 < a.max_events) {  // the next event is processed in this launch: its new events
+      if (en.type != EV_END) ev_draws(e);
+      const int pushed = ev_env_push(sm, e, qb, en.type, en.cell, en.time, n_next > 0);  // Simulator.hs:101-128
+      q_overflow = pushed == PEND_OVERFLOW;
+      pend_slot = q_overflow ? -1 : pushed;
+    }
     DCA_CLK(c4);
-    cta_barrier();  // B1
-    DCA_CLKB(c5);
+    DCA_CLK(c5);
     DCA_ACC(0, c0, c1); DCA_ACC(1, c1, c2); DCA_ACC(2, c2, c3); DCA_ACC(3, c3, c4); DCA_ACC(4, c4, c5); DCA_ACC(5, c0, c5);
-    if (stop != ST_RUNNING) { ++it; break; }
+    DCA_SUB(0, c3, s0); DCA_SUB(1, s0, s1); DCA_SUB(2, s1, s2); DCA_SUB(3, s2, s3); DCA_SUB(4, s3, s4); DCA_SUB(5, s4, s5); DCA_SUB(6, s5, c4);
+    if (stop != ST_RUNNING) break;
   }
 #ifdef DCA_PHASE_CLOCK
-  if (lane == 0)
+  if (lane == 0) {
     for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[3][i], (unsigned long long)ph[i]);
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_phase[4][i], (unsigned long long)sub[i]);
+  }
 #endif
   cta_barrier();
   stage_out(sm, g);
   if (lane == 0) {
-    const Ev& ev = sm.ev[it & 1];
+    const Ev& ev = sm.ev[cur];  // the next event to process (popped, its new events not pushed yet)
 #pragma unroll
     for (int k = 0; k < 8; ++k) g->stats[k] = e.stats[k];
     g->n_end = e.n_end; g->next_id = e.next_id; g->ndraws = e.ndraws;

@@ -15,7 +15,7 @@ n_ev = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
 warm = int(sys.argv[3]) if len(sys.argv) > 3 else 20000
 with Replicas(Opt(n_replicas=n_rep, n_events=warm + n_ev, order="fast", rng="philox")) as s:
     s.run(warm)
-    out = (C.c_ulonglong * 32)()
+    out = (C.c_ulonglong * 48)()
     h = _ffi.load()
     h.dca_debug_phase(out, 1)
     ms = s.run(n_ev)
@@ -25,3 +25,5 @@ with Replicas(Opt(n_replicas=n_rep, n_events=warm + n_ev, order="fast", rng="phi
     for role in range(4):
         v = [out[role * 8 + i] / (n_rep * n_ev) for i in range(6)]
         print(("agent %d" % role if role < 3 else "event  "), "  ".join(f"{n} {x:7.0f}" for n, x in zip(names, v)))
+    subs = ["post", "rescans", "masks", "wait cnt2", "candidates", "stop rules", "push next"]
+    print("event warp, update phase:", "  ".join(f"{n} {out[4 * 8 + i] / (n_rep * n_ev):6.0f}" for i, n in enumerate(subs)))
