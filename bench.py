@@ -33,9 +33,22 @@ UNIT = "events/s"
 ALG_BYTES_PER_EVENT = 4 * 3479 * 4  # read+write of wNet and wGradCorr, SURVEY.md 8(d)
 
 
+def kernel_ceilings():
+    """What one `ncu --set full` capture of k_run_fast says about the limits that actually bind it (issue slots, the
+    shared-memory data pipe) and its real DRAM traffic: profiles/kernel_ceilings.json, written by tools/ncu_ceilings.py."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_ceilings.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
 def measured_traffic():
-    """DRAM bytes of one k_run_fast launch on the bench workload, from the committed ncu capture
-    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of `ncu --set full`)."""
+    """DRAM bytes of one k_run_fast launch on the bench workload (dram__bytes_read.sum + dram__bytes_write.sum of
+    `ncu --set full`; one state blob in and out per replica, whatever the number of events per launch)."""
+    c = kernel_ceilings()
+    if c and c.get("dram_bytes_per_launch"):
+        return float(c["dram_bytes_per_launch"]), c.get("source", "")
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
@@ -249,13 +262,21 @@ def main():
         ms += sims.run(n_ev)
         return ms
 
-    def step_e2e():
-        """the same step through the C ABI with HOST buffers: H2D of the parameters, run, D2H of the per-replica results"""
+    agents_out = None
+
+    def step_e2e(with_agents=False):
+        """the same step through the C ABI with HOST buffers: H2D of the parameters, run, D2H of the per-replica results
+        (status, iter, average reward, the 8 Stats counters) -- and, with_agents, of every replica's learned wNet and
+        wGradCorr (2 x 3479 floats per replica)"""
+        nonlocal agents_out
         h2d = sims.set_params(**host_params)
         sims.reset()
         sims.run(n_ev)
         summ = sims.read_summary()
         d2h = sum(v.nbytes for v in summ.values())
+        if with_agents:
+            agents_out = sims.read_agents(agents_out)
+            d2h += agents_out[0].nbytes + agents_out[1].nbytes + agents_out[2].nbytes
         return h2d, d2h, summ
 
     for _ in range(args.warmup):
@@ -304,7 +325,21 @@ def main():
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": events_all * args.steps / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+        e2e = {"value": events_all * args.steps / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "reads_back": "per-replica results: status, iter, average reward, the 8 Stats counters (blocking probabilities)"}
+        # variant: the learned weights of every replica cross PCIe too
+        step_e2e(True)
+        barrier()
+        t2 = time.perf_counter()
+        for _ in range(args.steps):
+            h2d_w, d2h_w, _ = step_e2e(True)
+        barrier()
+        tw = torch.tensor([time.perf_counter() - t2], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e["with_learned_weights"] = {"value": events_all * args.steps / tw.item(), "unit": UNIT, "h2d_bytes_per_step": int(h2d_w),
+                                       "d2h_bytes_per_step": int(d2h_w),
+                                       "reads_back": "the above plus wNet and wGradCorr of every replica (dca_read_agents)"}
 
     # the timed configuration against the oracle (every rank checks replicas of its own shard; the state on the
     # device is the one the last step left behind)
@@ -325,6 +360,16 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         traffic, traffic_src = measured_traffic()
+        ceil = kernel_ceilings()
+        binding = None
+        if ceil:
+            binding = {k: ceil.get(k) for k in ("issue_active_pct", "shared_pipe_pct_of_peak", "warp_instructions_per_event",
+                                                "shared_wavefronts_per_event", "eligible_warps_per_cycle", "pipe_alu_pct", "pipe_fma_pct",
+                                                "pipe_lsu_pct", "dram_throughput_pct", "registers_per_thread", "shared_mem_per_cta_kb",
+                                                "ctas_per_sm", "stalls_per_issued_instruction", "source")}
+            if ceil.get("warp_instructions_per_event"):
+                # 4 schedulers x 148 SMs x the SM clock issue slots per second: what 100 % issue utilisation would give
+                binding["events_per_s_at_full_issue_rate"] = 4 * 148 * 1.965e9 / ceil["warp_instructions_per_event"]
         per_gpu_run = n_rep * n_ev * args.steps / (run_ms_max / 1e3)  # the dominant kernel, per GPU
         achieved = per_gpu_run * ALG_BYTES_PER_EVENT / 1e9
         bp = float(st[2]) / (float(st[0]) + 1.0)
@@ -340,11 +385,13 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "dca::fast::k_run_fast<false>", "peak_source": peak_src, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": n_rep * n_ev * ALG_BYTES_PER_EVENT,
+                         "regime": "on-chip residency: NOT an HBM utilisation figure",
+                         "binding_ceilings": binding,
                          "note": "achieved = events/s/GPU x 55 664 algorithmic bytes (r+w of wNet, wGradCorr per event, Agent.hs:67-76) over the "
-                                 "kernel's own CUDA-event duration; the kernel keeps a replica's weights on chip (shared memory + tensor memory) for "
-                                 "the whole launch, so DRAM traffic is one state blob in and out per replica per launch and frac > 1 is "
-                                 "legitimate multi-event residency -- the binding limits are issue slots and the per-event dependency chain "
-                                 "(profiles/: smsp__issue_active, stall reasons)"},
+                                 "kernel's own CUDA-event duration, against the measured HBM peak as SURVEY.md 8(d) defines the fraction.  The "
+                                 "kernel keeps a replica's weights on chip (shared memory + tensor memory) for the whole launch, so real DRAM "
+                                 "traffic (`traffic`) is one state blob in and out per replica per launch and frac > 1 is multi-event residency, "
+                                 "not bandwidth; what binds is in `binding_ceilings` (ncu: issue slots, the shared-memory data pipe, stalls)"},
             "e2e": e2e,
             "gpu_launches": int(launches),
             "clocks": clocks,

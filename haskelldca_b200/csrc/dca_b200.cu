@@ -174,6 +174,7 @@ struct dca_handle {
   Summary* d_summary = nullptr;
   HostView* d_view = nullptr;
   StepOut* d_stepout = nullptr;
+  float* d_agents = nullptr;  // dca_read_agents: [2][chunk][3479] + [chunk] floats, allocated at first use
   std::string err;
   float last_ms = 0.f;
   long long launches = 0;
@@ -322,6 +323,7 @@ int dca_destroy(dca_handle* h) {
   cudaFree(h->d_mean_new); cudaFree(h->d_call_dur); cudaFree(h->d_call_dur_hoff); cudaFree(h->d_hoff_prob);
   cudaFree(h->d_a_net); cudaFree(h->d_a_avg); cudaFree(h->d_a_grad);
   cudaFree(h->d_tape_w); cudaFree(h->d_tape_l); cudaFree(h->d_tape_off);
+  cudaFree(h->d_agents);
   cudaFree(h->d_trace); cudaFree(h->d_sum); cudaFree(h->d_summary); cudaFree(h->d_view); cudaFree(h->d_stepout);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -794,6 +796,27 @@ int dca_read_summary(dca_handle* h, int32_t* status, int64_t* iter, float* avg_r
     if (avg_reward) avg_reward[i] = s[i].avg_reward;
     if (stats)
       for (int k = 0; k < 8; ++k) stats[(size_t)i * 8 + k] = s[i].stats[k];
+  }
+  return DCA_OK;
+}
+
+int dca_read_agents(dca_handle* h, float* wnet, float* wgrad, float* avg_reward) {
+  if (!h) return DCA_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  const int chunk = 4096;
+  const size_t per = (size_t)chunk * FREP;
+  if (!h->d_agents) CK(cudaMalloc(&h->d_agents, sizeof(float) * (2 * per + chunk)));
+  float *dw = h->d_agents, *dg = h->d_agents + per, *da = h->d_agents + 2 * per;
+  for (int first = 0; first < h->n; first += chunk) {
+    const int cnt = std::min(chunk, h->n - first);
+    k_unpack_agents<<<cnt, 256, 0, h->stream>>>(h->d_states, first, cnt, wnet ? dw : nullptr, wgrad ? dg : nullptr,
+                                                avg_reward ? da : nullptr);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (wnet) CK(cudaMemcpyAsync(wnet + (size_t)first * FREP, dw, sizeof(float) * (size_t)cnt * FREP, cudaMemcpyDeviceToHost, h->stream));
+    if (wgrad) CK(cudaMemcpyAsync(wgrad + (size_t)first * FREP, dg, sizeof(float) * (size_t)cnt * FREP, cudaMemcpyDeviceToHost, h->stream));
+    if (avg_reward) CK(cudaMemcpyAsync(avg_reward + first, da, sizeof(float) * cnt, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));  // (the device buffers are reused by the next chunk)
   }
   return DCA_OK;
 }

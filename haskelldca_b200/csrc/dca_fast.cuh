@@ -787,7 +787,7 @@ __device__ __forceinline__ void ev_candidates(const SmemF& sm, Ev& ev, const int
   const int lane = lane_id();
   const int cell = ev.cell;
   const bool is_end = ev.type == EV_END;
-  const int pos = c_tab.pos[cell];
+  const int pos = pos_of(cell);
   const unsigned long long n4 = c_tab.n4excl[cell], n2 = c_tab.n2incl[cell];
   uint32_t m[3];
   if (is_end) {  // inuseChs, Gridfuncs.hs:86-87
@@ -1170,7 +1170,7 @@ __device__ __noinline__ void ev_hashes(const SmemF& sm, unsigned long long& hg_o
 #pragma unroll 1
   for (int i = lane_id(); i < NFEAT * NCELL; i += 32) {
     const int cell = i / NFEAT, f = i - cell * NFEAT;
-    hf += (unsigned long long)sm.x[f * PLANE + c_tab.pos[cell]] * mix64(0x10000ULL + (unsigned long long)i);
+    hf += (unsigned long long)sm.x[f * PLANE + pos_of(cell)] * mix64(0x10000ULL + (unsigned long long)i);
     if (f < NCH && ((sm.grid[cell][f >> 5] >> (f & 31)) & 1u)) hg += mix64((unsigned long long)(cell * NCH + f));
   }
   for (int off = 16; off > 0; off >>= 1) {

@@ -53,6 +53,11 @@ struct Scratch {
   double ev_time_prev;
   int flag;
   uint8_t cand[72];
+  // the products float(x_i) * wNet_i and float(x_i) * wGradCorr_i of the CURRENT state in flatten order i = cell * 71 + f,
+  // formed by all threads once per event: every dense right fold of the event (V(s), x.wGradCorr, one per candidate)
+  // then reads them as broadcasts and only re-forms the <= 61 terms its afterstate changes
+  float prod_w[NFEAT * NCELL + 1];
+  float prod_g[NFEAT * NCELL + 1];
 };
 
 struct Smem {
@@ -64,6 +69,9 @@ struct Smem {
 // small helpers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+// offset of cell (r, c) = r * 7 + c inside a padded plane: r * 8 + c = cell + cell / 7  (arithmetic: a constant-memory
+// table indexed differently by every lane of a warp is served one address at a time)
+__device__ __forceinline__ int pos_of(const int cell) { return cell + ((cell * 37) >> 8); }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
 // 7 mask bits -> 7 bytes of 0/1 (uint2, byte c = bit c)
@@ -343,7 +351,7 @@ __device__ __forceinline__ void environment_step(RepState& s, QRegs& q, Rng& rng
 __device__ __forceinline__ int build_candidates(Smem& sm, int cell, bool is_end) {
   RepState& s = sm.s;
   const int lane = lane_id();
-  const int pos = c_tab.pos[cell];
+  const int pos = pos_of(cell);
   uint32_t m[3];
   if (is_end) {  // inuseChs, Gridfuncs.hs:86-87
     m[0] = s.grid[cell][0]; m[1] = s.grid[cell][1]; m[2] = s.grid[cell][2];
@@ -411,8 +419,8 @@ __device__ __forceinline__ unsigned long long elig_change_mask(const RepState& s
   const int lane = lane_id();
   const uint8_t want = is_end ? 1 : 0;
   int c0 = lane, c1 = lane + 32;
-  bool b0 = ((n2mask >> c0) & 1ULL) && s.cnt2[ch * PLANE + c_tab.pos[c0]] == want;
-  bool b1 = (c1 < NCELL) && ((n2mask >> c1) & 1ULL) && s.cnt2[ch * PLANE + c_tab.pos[c1]] == want;
+  bool b0 = ((n2mask >> c0) & 1ULL) && s.cnt2[ch * PLANE + pos_of(c0)] == want;
+  bool b1 = (c1 < NCELL) && ((n2mask >> c1) & 1ULL) && s.cnt2[ch * PLANE + pos_of(c1)] == want;
   unsigned lo = __ballot_sync(0xffffffffu, b0), hi = __ballot_sync(0xffffffffu, b1);
   return (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
@@ -458,27 +466,63 @@ __device__ __forceinline__ void apply_action(Smem& sm, int cell, bool is_end, in
 // ---------------------------------------------------------------------------
 // REF order: reference-literal arithmetic (Accelerate Interpreter)
 // ---------------------------------------------------------------------------
-// dense right fold over flatten order i = cell*71 + f, i = 3478..0, of
-// float(afrep[i]) * w[i]; the afterstate of candidate `ch` (or the state itself
-// if ch < 0) is formed on the fly.  One thread.
-__device__ __noinline__ float ref_dense_dot(const Smem& sm, const float* wv, int ch, bool is_end) {
+// The dense dots of the REF order are right folds over flatten order i = cell*71 + f, i = 3478..0, of
+// float(afrep[i]) * w[i] with products and sums rounded separately (the Accelerate Interpreter).  The additions of a
+// fold are inherently sequential; the products are not: all threads form them once per event (ref_products), and a
+// fold is then 3479 dependent FADDs fed by shared-memory broadcasts.
+__device__ __forceinline__ void ref_products(Smem& sm) {
+  const RepState& s = sm.s;
+  for (int k = threadIdx.x; k < NFEAT * NCELL; k += blockDim.x) {
+    const int f = k / NCELL, cell = k - f * NCELL;
+    const int off = f * PLANE + pos_of(cell);
+    const float x = (float)s.x[off];
+    sm.t.prod_w[cell * NFEAT + f] = __fmul_rn(x, s.w[off]);
+    sm.t.prod_g[cell * NFEAT + f] = __fmul_rn(x, s.wg[off]);
+  }
+}
+// x . w of the current state: p0 + (p1 + (... + (p3478 + 0)))
+__device__ __noinline__ float ref_fold_plain(const float* p) {
+  float acc = 0.0f;
+  static_assert((NFEAT * NCELL) % 7 == 0, "the fold loads seven products at a time");
+#pragma unroll 2
+  for (int i0 = NFEAT * NCELL - 7; i0 >= 0; i0 -= 7) {
+    float v[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = p[i0 + k];
+#pragma unroll
+    for (int k = 6; k >= 0; --k) acc = __fadd_rn(v[k], acc);
+  }
+  return acc;
+}
+// the same fold for the afterstate of candidate `ch` (incAfterStateFreps, Gridfuncs.hs:186-252, never materialised):
+// per cell the n_elig term (f = 70) and the channel's own term (f = ch) are re-formed when the action changes them, the
+// other 69 terms are the current state's products.  One thread; the threads of a warp stay in lock step (the inner
+// loop is the same for every channel, the re-formed term is selected by a compare).
+__device__ __noinline__ float ref_fold_candidate(const Smem& sm, const int ch, const bool is_end) {
   const RepState& s = sm.s;
   const unsigned long long n4 = sm.t.n4mask, n2 = sm.t.n2mask;
   const int diff = is_end ? -1 : 1;
   const uint8_t want = is_end ? 1 : 0;
   float acc = 0.0f;
+#pragma unroll 1
   for (int cell = NCELL - 1; cell >= 0; --cell) {
-    const int pos = c_tab.pos[cell];
-    int d_in = 0, d_el = 0;
-    if (ch >= 0) {
-      d_in = ((n4 >> cell) & 1ULL) ? diff : 0;
-      d_el = (((n2 >> cell) & 1ULL) && s.cnt2[ch * PLANE + pos] == want) ? -diff : 0;
-    }
-    for (int f = NFEAT - 1; f >= 0; --f) {
-      int xv = s.x[f * PLANE + pos];
-      if (f == ch) xv += d_in;
-      if (f == NCH) xv += d_el;
-      acc = __fadd_rn(__fmul_rn((float)xv, wv[f * PLANE + pos]), acc);
+    const int pos = cell + (cell * 37 >> 8);  // (cell / 7) * 8 + cell % 7 for cell < 49
+    const float* p = &sm.t.prod_w[cell * NFEAT];
+    float t70 = p[NCH];
+    if (((n2 >> cell) & 1ULL) && s.cnt2[ch * PLANE + pos] == want)  // Gridfuncs.hs:220-252
+      t70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] - diff), s.w[NCH * PLANE + pos]);
+    float tch = p[ch];
+    if ((n4 >> cell) & 1ULL)                                        // Gridfuncs.hs:212-217
+      tch = __fmul_rn((float)((int)s.x[ch * PLANE + pos] + diff), s.w[ch * PLANE + pos]);
+    acc = __fadd_rn(t70, acc);
+    static_assert(NCH % 10 == 0, "the fold loads ten products at a time");
+#pragma unroll
+    for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {  // ten loads in flight, then ten dependent additions
+      float v[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) v[k] = p[f0 + k];
+#pragma unroll
+      for (int k = 9; k >= 0; --k) acc = __fadd_rn((f0 + k) == ch ? tch : v[k], acc);
     }
   }
   return acc;
@@ -493,7 +537,7 @@ __device__ __forceinline__ void ref_dense_update(Smem& sm) {
   const unsigned long long n4 = t.n4mask, chg = t.chgmask;
   for (int i = threadIdx.x; i < NFEAT * NCELL; i += blockDim.x) {
     const int f = i / NCELL, cell = i - f * NCELL;
-    const int off = f * PLANE + c_tab.pos[cell];
+    const int off = f * PLANE + pos_of(cell);
     const int xn = s.x[off];
     int xo = xn;
     if (act_ch >= 0) {
@@ -523,7 +567,7 @@ __device__ __forceinline__ void state_hashes(Smem& sm) {
   unsigned long long hg = 0, hf = 0;
   for (int i = threadIdx.x; i < NFEAT * NCELL; i += blockDim.x) {
     const int cell = i / NFEAT, f = i - cell * NFEAT;
-    hf += (unsigned long long)s.x[f * PLANE + c_tab.pos[cell]] * mix64(0x10000ULL + (unsigned long long)i);
+    hf += (unsigned long long)s.x[f * PLANE + pos_of(cell)] * mix64(0x10000ULL + (unsigned long long)i);
     if (f < NCH && ((s.grid[cell][f >> 5] >> (f & 31)) & 1u)) hg += mix64((unsigned long long)(cell * NCH + f));
   }
   for (int off = 16; off > 0; off >>= 1) {
@@ -628,11 +672,16 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     __syncthreads();
     const int n = t.ncand;
     const bool is_end = t.ev_is_end;
+    ref_products(sm);
+    __syncthreads();
     // candidates on threads 0..n-1, V(s) and x.wg on the last two threads
     for (int k = threadIdx.x; k < n; k += nthreads - 2)
-      if (threadIdx.x < nthreads - 2) t.q[k] = ref_dense_dot(sm, s.w, t.cand[k], is_end);
-    if (threadIdx.x == nthreads - 1) t.val = ref_dense_dot(sm, s.w, -1, false);
-    if (threadIdx.x == nthreads - 2) t.dotg = ref_dense_dot(sm, s.wg, -1, false);
+      if (threadIdx.x < nthreads - 2) t.q[k] = ref_fold_candidate(sm, t.cand[k], is_end);
+    if (threadIdx.x >= nthreads - 2) {
+      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : t.prod_g);
+      if (threadIdx.x == nthreads - 1) t.val = v;
+      else t.dotg = v;
+    }
     __syncthreads();
   }
   if (wid == 0) {
@@ -773,7 +822,7 @@ __global__ void k_init(InitArgs a) {
   for (int i = lane; i < (int)(sizeof(RepState) / 16); i += 32) p[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
   // frep = featureRep emptyGrid: in-use counts 0, n_elig 70 everywhere
-  for (int cell = lane; cell < NCELL; cell += 32) s.x[NCH * PLANE + c_tab.pos[cell]] = NCH;
+  for (int cell = lane; cell < NCELL; cell += 32) s.x[NCH * PLANE + pos_of(cell)] = NCH;
   for (int i = lane; i < QCAP; i += 32) {
     s.q_time[i] = CUDART_INF;
     s.q_key[i] = (uint16_t)(((i < QNEW ? i : 0) << 7) | 127);
@@ -844,15 +893,15 @@ __device__ __forceinline__ void feature_rep_from_grid(RepState& s) {
       m2 &= m2 - 1;
       in2 += (s.grid[n][wsel] >> bit) & 1u;
     }
-    s.x[ch * PLANE + c_tab.pos[cell]] = (uint8_t)in4;
-    s.cnt2[ch * PLANE + c_tab.pos[cell]] = (uint8_t)in2;
+    s.x[ch * PLANE + pos_of(cell)] = (uint8_t)in4;
+    s.cnt2[ch * PLANE + pos_of(cell)] = (uint8_t)in2;
   }
   __syncthreads();
   for (int cell = threadIdx.x; cell < NCELL; cell += blockDim.x) {
     int ne = 0, nc = 0;
-    for (int ch = 0; ch < NCH; ++ch) ne += s.cnt2[ch * PLANE + c_tab.pos[cell]] == 0;
+    for (int ch = 0; ch < NCH; ++ch) ne += s.cnt2[ch * PLANE + pos_of(cell)] == 0;
     nc = __popc(s.grid[cell][0]) + __popc(s.grid[cell][1]) + __popc(s.grid[cell][2]);
-    s.x[NCH * PLANE + c_tab.pos[cell]] = (uint8_t)ne;
+    s.x[NCH * PLANE + pos_of(cell)] = (uint8_t)ne;
     atomicAdd(&s.ncalls, nc);
   }
   __syncthreads();
@@ -912,10 +961,15 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   }
   const int n = t.ncand;
   {
+    ref_products(sm);
+    __syncthreads();
     for (int k = threadIdx.x; k < n; k += nthreads - 2)
-      if (threadIdx.x < nthreads - 2) t.q[k] = ref_dense_dot(sm, s.w, t.cand[k], is_end);
-    if (threadIdx.x == nthreads - 1) t.val = ref_dense_dot(sm, s.w, -1, false);
-    if (threadIdx.x == nthreads - 2) t.dotg = ref_dense_dot(sm, s.wg, -1, false);
+      if (threadIdx.x < nthreads - 2) t.q[k] = ref_fold_candidate(sm, t.cand[k], is_end);
+    if (threadIdx.x >= nthreads - 2) {
+      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : t.prod_g);
+      if (threadIdx.x == nthreads - 1) t.val = v;
+      else t.dotg = v;
+    }
     __syncthreads();
   }
   if (wid == 0) {
@@ -983,13 +1037,13 @@ __global__ void k_gf_load_grid(RepState* st, const uint8_t* grid) {
 __global__ void k_gf_store_frep(const RepState* st, long long* frep) {
   for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
     int cell = i / NFEAT, f = i - cell * NFEAT;
-    frep[i] = st->x[f * PLANE + c_tab.pos[cell]];
+    frep[i] = st->x[f * PLANE + pos_of(cell)];
   }
 }
 __global__ void k_gf_load_frep(RepState* st, const long long* frep) {
   for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
     int cell = i / NFEAT, f = i - cell * NFEAT;
-    st->x[f * PLANE + c_tab.pos[cell]] = (uint8_t)frep[i];
+    st->x[f * PLANE + pos_of(cell)] = (uint8_t)frep[i];
   }
 }
 // eligible (is_end = 0) / in-use (is_end = 1) channels, ascending
@@ -999,7 +1053,7 @@ __global__ void k_gf_chs(const RepState* st, int cell, int is_end, long long* ch
     n = 0;
     for (int ch = 0; ch < NCH; ++ch) {
       bool on = is_end ? ((st->grid[cell][ch >> 5] >> (ch & 31)) & 1u)
-                       : (st->cnt2[ch * PLANE + c_tab.pos[cell]] == 0);
+                       : (st->cnt2[ch * PLANE + pos_of(cell)] == 0);
       if (on) chs[n++] = ch;
     }
     *n_out = n;
@@ -1018,7 +1072,7 @@ __global__ void k_gf_inc_afterstate_freps(const RepState* st, int cell, int is_e
     int ch = (int)chs[k];
     long long v = frep[i];  // the caller's frep (it need not be featureRep grid), Gridfuncs.hs:206
     if (f == ch && ((n4 >> c2) & 1ULL)) v += diff;
-    if (f == NCH && ((n2 >> c2) & 1ULL) && st->cnt2[ch * PLANE + c_tab.pos[c2]] == want) v -= diff;
+    if (f == NCH && ((n2 >> c2) & 1ULL) && st->cnt2[ch * PLANE + pos_of(c2)] == want) v -= diff;
     out[idx] = v;
   }
 }
@@ -1045,7 +1099,7 @@ struct HostView {  // unpacked replica state in the reference's layouts
 __global__ void k_unpack(const RepState* st, HostView* hv) {
   for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
     int cell = i / NFEAT, f = i - cell * NFEAT;
-    int off = f * PLANE + c_tab.pos[cell];
+    int off = f * PLANE + pos_of(cell);
     hv->frep[i] = st->x[off];
     hv->w[i] = st->w[off];
     hv->wg[i] = st->wg[off];
@@ -1059,10 +1113,24 @@ __global__ void k_unpack(const RepState* st, HostView* hv) {
 __global__ void k_pack_weights(RepState* st, const float* w, const float* wg) {
   for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
     int cell = i / NFEAT, f = i - cell * NFEAT;
-    int off = f * PLANE + c_tab.pos[cell];
+    int off = f * PLANE + pos_of(cell);
     if (w) st->w[off] = w[i];
     if (wg) st->wg[off] = wg[i];
   }
+}
+
+// wNet / wGradCorr of replicas [first, first + count) in the reference's flatten order (either output may be null)
+__global__ void k_unpack_agents(const RepState* states, int first, int count, float* w, float* wg, float* avg) {
+  const int rep = blockIdx.x;
+  if (rep >= count) return;
+  const RepState& s = states[first + rep];
+  for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
+    const int cell = i / NFEAT, f = i - cell * NFEAT;
+    const int off = f * PLANE + pos_of(cell);
+    if (w) w[(size_t)rep * FREP + i] = s.w[off];
+    if (wg) wg[(size_t)rep * FREP + i] = s.wg[off];
+  }
+  if (avg && threadIdx.x == 0) avg[rep] = s.avg_reward;
 }
 
 struct Summary {

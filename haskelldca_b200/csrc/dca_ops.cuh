@@ -20,7 +20,23 @@ struct DotScratch {
   float P[72];
   float W[4];
   float out;
+  float out3[3];
+  float prod[3][FREP + 1];  // REF order: the products of up to three dots, formed by all threads before the serial folds
 };
+// right fold p0 + (p1 + (... + (p3478 + 0))) of products already in shared memory (one thread)
+__device__ __forceinline__ float ref_fold(const float* p) {
+  float acc = 0.0f;
+  static_assert(FREP % 7 == 0, "the fold loads seven products at a time");
+#pragma unroll 2
+  for (int i0 = FREP - 7; i0 >= 0; i0 -= 7) {
+    float v[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) v[k] = p[i0 + k];
+#pragma unroll
+    for (int k = 6; k >= 0; --k) acc = __fadd_rn(v[k], acc);
+  }
+  return acc;
+}
 
 __device__ __forceinline__ int fidx(int r, int c, int f) { return (r * COLS + c) * NFEAT + f; }
 
@@ -43,12 +59,10 @@ __device__ __forceinline__ float rowdot_flat(const long long* x, const float* w,
 __device__ __forceinline__ float cta_dense_dot(DotScratch& t, int order, bool g_tree, const long long* x,
                                                const float* w) {
   __syncthreads();
-  if (order == ORDER_REF) {
-    if (threadIdx.x == 0) {
-      float acc = 0.0f;
-      for (int i = FREP - 1; i >= 0; --i) acc = __fadd_rn(__fmul_rn((float)x[i], w[i]), acc);
-      t.out = acc;
-    }
+  if (order == ORDER_REF) {  // products by all threads, the (inherently sequential) additions by one
+    for (int i = threadIdx.x; i < FREP; i += blockDim.x) t.prod[0][i] = __fmul_rn((float)x[i], w[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) t.out = ref_fold(t.prod[0]);
     __syncthreads();
     return t.out;
   }
@@ -129,7 +143,7 @@ __global__ void k_afterstates_dev(const RepState* st, int cell, int is_end, cons
     const int ch = (int)chs[k];
     long long v = frep[i];  // Gridfuncs.hs:206
     if (f == ch && ((n4 >> c2) & 1ULL)) v += diff;                                                       // :212-217
-    if (f == NCH && ((n2 >> c2) & 1ULL) && st->cnt2[ch * PLANE + c_tab.pos[c2]] == want) v -= diff;      // :220-252
+    if (f == NCH && ((n2 >> c2) & 1ULL) && st->cnt2[ch * PLANE + pos_of(c2)] == want) v -= diff;      // :220-252
     out[idx] = v;
   }
 }
@@ -169,9 +183,25 @@ struct BackwardOut {
 __device__ __forceinline__ void backward_body(DotScratch& t, int order, float alpha_net, float alpha_avg, float alpha_grad,
                                               const long long* frep, const long long* next_frep, float reward,
                                               float avg_reward, float* w, float* wg, BackwardOut* out) {
-  const float val = cta_dense_dot(t, order, false, frep, w);           // :62
-  const float next_val = cta_dense_dot(t, order, false, next_frep, w); // :63
-  const float dot = cta_dense_dot(t, order, true, frep, wg);           // :66
+  float val, next_val, dot;
+  if (order == ORDER_REF) {  // the three right folds run side by side on three threads
+    __syncthreads();
+    for (int i = threadIdx.x; i < FREP; i += blockDim.x) {
+      const float x = (float)frep[i], xn = (float)next_frep[i];
+      t.prod[0][i] = __fmul_rn(x, w[i]);
+      t.prod[1][i] = __fmul_rn(xn, w[i]);
+      t.prod[2][i] = __fmul_rn(x, wg[i]);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && threadIdx.x < 96) t.out3[threadIdx.x >> 5] = ref_fold(t.prod[threadIdx.x >> 5]);
+    __syncthreads();
+    val = t.out3[0]; next_val = t.out3[1]; dot = t.out3[2];  // :62, :63, :66
+    __syncthreads();
+  } else {
+    val = cta_dense_dot(t, order, false, frep, w);           // :62
+    next_val = cta_dense_dot(t, order, false, next_frep, w); // :63
+    dot = cta_dense_dot(t, order, true, frep, wg);           // :66
+  }
   const float td = __fsub_rn(__fadd_rn(__fsub_rn(reward, avg_reward), next_val), val);  // :65
   const float c = __fmul_rn(-2.0f, alpha_net);                                          // :67
   const float ctd = __fmul_rn(c, td), cavg = __fmul_rn(c, avg_reward), cdot = __fmul_rn(c, dot);

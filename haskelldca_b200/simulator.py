@@ -206,6 +206,15 @@ class Replicas:
         _ffi.check(_ffi.load().dca_read_summary(self.h, _ffi.ptr(status), _ffi.ptr(it), _ffi.ptr(avg), _ffi.ptr(st)), self.h)
         return dict(status=status, iter=it, avg_reward=avg, stats=st)
 
+    def read_agents(self, out=None):
+        """The learned agents of all replicas: (wnet [n, 3479], wgrad [n, 3479], avg_reward [n]) in the reference's
+        flatten order.  `out` = preallocated (pinned) arrays to fill, e.g. from a previous call."""
+        if out is None:
+            out = (np.empty((self.n, FREP_SIZE), np.float32), np.empty((self.n, FREP_SIZE), np.float32), np.empty(self.n, np.float32))
+        w, wg, avg = out
+        _ffi.check(_ffi.load().dca_read_agents(self.h, _ffi.ptr(w), _ffi.ptr(wg), _ffi.ptr(avg)), self.h)
+        return w, wg, avg
+
     def sum_stats(self):
         """int64[10]: summed Stats counters, events processed, failed replicas; plus its device address."""
         out = np.zeros(10, dtype=np.int64)

@@ -227,6 +227,10 @@ int dca_read_trace(dca_handle *h, int32_t replica, dca_trace *out, size_t cap, s
 /* bulk: per-replica arrays of length n_replicas (any may be NULL) */
 int dca_read_summary(dca_handle *h, int32_t *status, int64_t *iter, float *avg_reward,
                      int64_t *stats /* [n_replicas][8] */);
+/* bulk: the learned agents of ALL replicas in the reference's flatten order -- wnet / wgrad are
+ * [n_replicas][3479] floats, avg_reward [n_replicas] (any may be NULL).  Unpacked on the device, copied
+ * in chunks of 4096 replicas. */
+int dca_read_agents(dca_handle *h, float *wnet, float *wgrad, float *avg_reward);
 /* device-side sum over replicas: out[0..7] = stats, out[8] = events processed,
  * out[9] = replicas not RUNNING/SUCCESS.  *dev_ptr (optional) receives the device
  * address of the same int64[10] so a caller can all-reduce it across GPUs (NCCL). */
