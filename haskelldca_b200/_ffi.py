@@ -48,6 +48,8 @@ class Config(C.Structure):
         ("alpha_net_v", C.c_void_p),
         ("alpha_avg_v", C.c_void_p),
         ("alpha_grad_v", C.c_void_p),
+        ("hoff_lookahead", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 

@@ -341,6 +341,8 @@ int dca_create(const dca_config* cfg, dca_handle** out) {
     return fail(h, DCA_ERR_ARG, "dca_create: bad order");
   if (cfg->rng_mode != DCA_RNG_TAPE && cfg->rng_mode != DCA_RNG_PHILOX)
     return fail(h, DCA_ERR_ARG, "dca_create: bad rng_mode");
+  if (cfg->hoff_lookahead && cfg->order != DCA_ORDER_REF)
+    return fail(h, DCA_ERR_ARG, "dca_create: hoff_lookahead is implemented for DCA_ORDER_REF only (the FAST kernel has no look-ahead path yet)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(h, DCA_ERR_NO_DEVICE, "dca_create: no CUDA device (there is no CPU fallback)");
@@ -503,6 +505,7 @@ int dca_run(dca_handle* h, int64_t max_events) {
   a.tape_off = h->d_tape_off;
   a.trace = h->d_trace;
   a.trace_cap = h->cfg.trace_capacity;
+  a.lookahead = h->cfg.hoff_lookahead;
   const bool trace = h->d_trace != nullptr;
   // (the TRACE instantiation of the fused FAST kernel also serves the verify flags: it has the extra per-event barrier)
   const bool trace_fast = trace || a.verify_rc || a.verify_nb;

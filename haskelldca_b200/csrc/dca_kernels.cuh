@@ -36,8 +36,11 @@ struct RunArgs {
   const unsigned long long* tape_off;  // [n_replicas + 1]
   TraceRec* trace;                  // [n_replicas][trace_cap] or null
   int trace_cap;
+  int lookahead;                    // hand-off look-ahead (extension; REF-order kernel only)
 };
 
+constexpr int LA_PAIRS = 1008;  // 8 rounds of 126 folding threads
+constexpr int LA_NONE = 255;
 // Scratch that lives next to RepState in shared memory (reference-order kernels).
 struct Scratch {
   float q[72];     // afterstate values of the candidates
@@ -58,6 +61,12 @@ struct Scratch {
   // then reads them as broadcasts and only re-forms the <= 61 terms its afterstate changes
   float prod_w[NFEAT * NCELL + 1];
   float prod_g[NFEAT * NCELL + 1];
+  // hand-off look-ahead (extension): the (channel to free, channel to assign in the target cell) pairs of one round
+  float q_plain[72];           // V(afterstate_k): the TD target stays the real next state
+  float pair_q[LA_PAIRS];
+  uint8_t pair_k[LA_PAIRS];    // index into cand
+  uint8_t pair_h[LA_PAIRS];    // channel in the target cell, LA_NONE = the plain afterstate of the END
+  int la_npairs, la_knext;
 };
 
 struct Smem {
@@ -528,6 +537,124 @@ __device__ __noinline__ float ref_fold_candidate(const Smem& sm, const int ch, c
   return acc;
 }
 
+// Hand-off look-ahead (extension, specified at dca_config.hoff_lookahead in include/dca_b200.h): the dense right fold of the
+// state after END `ch1` at `cell` AND, if ch2 >= 0, the HOFF arrival taking `ch2` at `cell2` on that afterstate.
+// Per cell the n_elig term, the term of ch1 and the term of ch2 are re-formed when the two actions change them:
+//   in-use features: ch1 loses its user at cell (-1 on N4(cell) \ {cell}), ch2 gains one at cell2 (+1 on N4(cell2) \ {cell2});
+//   n_elig: +1 where ch1 becomes eligible (cnt2[ch1] == 1 within N2(cell) u {cell}), then -1 where ch2 was eligible on
+//   that afterstate within N2(cell2) u {cell2} (cnt2 of ch2 after the END: one less inside N2(cell) if ch2 == ch1).
+__device__ __noinline__ float ref_fold_two(const Smem& sm, const int cell1, const int ch1, const int cell2, const int ch2) {
+  const RepState& s = sm.s;
+  const unsigned long long n4a = c_tab.n4excl[cell1], n2a = c_tab.n2incl[cell1];
+  const unsigned long long n4b = ch2 >= 0 ? c_tab.n4excl[cell2] : 0ULL, n2b = ch2 >= 0 ? c_tab.n2incl[cell2] : 0ULL;
+  const int c2 = ch2 >= 0 ? ch2 : ch1;  // (no second action: its masks are empty)
+  float acc = 0.0f;
+#pragma unroll 1
+  for (int cell = NCELL - 1; cell >= 0; --cell) {
+    const int pos = pos_of(cell);
+    const float* p = &sm.t.prod_w[cell * NFEAT];
+    const bool in2a = (n2a >> cell) & 1ULL, in2b = (n2b >> cell) & 1ULL;
+    int d70 = 0;
+    if (in2a && s.cnt2[ch1 * PLANE + pos] == 1) d70 += 1;
+    if (in2b && (int)s.cnt2[c2 * PLANE + pos] - ((c2 == ch1 && in2a) ? 1 : 0) == 0) d70 -= 1;
+    float t70 = p[NCH];
+    if (d70 != 0) t70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] + d70), s.w[NCH * PLANE + pos]);
+    const int d1 = (((n4a >> cell) & 1ULL) ? -1 : 0) + ((c2 == ch1 && ((n4b >> cell) & 1ULL)) ? 1 : 0);
+    float t1 = p[ch1];
+    if (d1 != 0) t1 = __fmul_rn((float)((int)s.x[ch1 * PLANE + pos] + d1), s.w[ch1 * PLANE + pos]);
+    float t2 = p[c2];
+    if (c2 != ch1 && ((n4b >> cell) & 1ULL)) t2 = __fmul_rn((float)((int)s.x[c2 * PLANE + pos] + 1), s.w[c2 * PLANE + pos]);
+    acc = __fadd_rn(t70, acc);
+#pragma unroll
+    for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {
+      float v[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) v[k] = p[f0 + k];
+#pragma unroll
+      for (int k = 9; k >= 0; --k) {
+        const int f = f0 + k;
+        acc = __fadd_rn(f == ch1 ? t1 : (f == c2 ? t2 : v[k]), acc);
+      }
+    }
+  }
+  return acc;
+}
+
+// the look-ahead values of all candidates of a hand-off END: t.q[k] (selection) and t.q_plain[k] (TD target).  All threads.
+__device__ __forceinline__ void lookahead_folds(Smem& sm, const int n, const int cell1, const int cell2) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const int lane = lane_id(), wid = warp_id(), nthreads = blockDim.x;
+  const int pos2 = pos_of(cell2);
+  int k0 = 0;
+  bool first_round = true;
+  while (k0 < n) {  // uniform
+    if (wid == 0) {
+      // channels eligible at the target cell on the CURRENT grid; freeing k adds k itself when the departing call was
+      // its only user within distance 2 of the target (the target is within distance 2 of the departure cell)
+      uint32_t e0[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int h = 32 * j + lane;
+        e0[j] = __ballot_sync(0xffffffffu, h < NCH && s.cnt2[h * PLANE + pos2] == 0);
+      }
+      int np = 0, k = k0;
+      for (; k < n; ++k) {
+        const int ch = t.cand[k];
+        uint32_t m[3] = {e0[0], e0[1], e0[2]};
+        if (s.cnt2[ch * PLANE + pos2] == 1) m[ch >> 5] |= 1u << (ch & 31);
+        const int mk = __popc(m[0]) + __popc(m[1]) + __popc(m[2]);
+        if (np + 1 + mk > LA_PAIRS) break;
+        if (lane == 0) { t.pair_k[np] = (uint8_t)k; t.pair_h[np] = (uint8_t)LA_NONE; }
+        int base = np + 1;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if ((m[j] >> lane) & 1u) {
+            const int at = base + __popc(m[j] & ((1u << lane) - 1u));
+            t.pair_k[at] = (uint8_t)k;
+            t.pair_h[at] = (uint8_t)(32 * j + lane);
+          }
+          base += __popc(m[j]);
+        }
+        np = base;
+      }
+      if (lane == 0) { t.la_npairs = np; t.la_knext = k; }
+    }
+    __syncthreads();
+    const int np = t.la_npairs;
+    if (threadIdx.x < nthreads - 2) {
+      for (int p = threadIdx.x; p < np; p += nthreads - 2) {
+        const int h = t.pair_h[p];
+        t.pair_q[p] = ref_fold_two(sm, cell1, t.cand[t.pair_k[p]], cell2, h == LA_NONE ? -1 : h);
+      }
+    } else if (first_round) {  // V(s) and x.wGradCorr of the current state, once
+      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : t.prod_g);
+      if (threadIdx.x == nthreads - 1) t.val = v;
+      else t.dotg = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // per candidate: the plain value, and the maximum over its pairs (left fold with >, ascending h)
+      int p = 0;
+      while (p < np) {
+        const int k = t.pair_k[p];
+        const float plain = t.pair_q[p++];
+        float best = plain;
+        bool have = false;
+        while (p < np && t.pair_k[p] == k) {
+          const float v = t.pair_q[p++];
+          if (!have) { best = v; have = true; }
+          else if (v > best) best = v;
+        }
+        t.q_plain[k] = plain;
+        t.q[k] = best;
+      }
+    }
+    __syncthreads();
+    k0 = t.la_knext;
+    first_round = false;
+  }
+}
+
 // elementwise TDC update, Agent.hs:67-76, each operation rounded separately
 __device__ __forceinline__ void ref_dense_update(Smem& sm) {
   RepState& s = sm.s;
@@ -674,14 +801,21 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     const bool is_end = t.ev_is_end;
     ref_products(sm);
     __syncthreads();
-    // candidates on threads 0..n-1, V(s) and x.wg on the last two threads
-    for (int k = threadIdx.x; k < n; k += nthreads - 2)
-      if (threadIdx.x < nthreads - 2) t.q[k] = ref_fold_candidate(sm, t.cand[k], is_end);
-    if (threadIdx.x >= nthreads - 2) {
-      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : t.prod_g);
-      if (threadIdx.x == nthreads - 1) t.val = v;
-      else t.dotg = v;
+    const bool la = a.lookahead && is_end && n > 0 && s.ev_hoff != HOFF_NONE;  // uniform: the departure half of a hand-off
+    if (la) {
+      lookahead_folds(sm, n, t.ev_cell, s.ev_hoff);
+    } else {
+      // candidates on threads 0..n-1, V(s) and x.wg on the last two threads
+      for (int k = threadIdx.x; k < n; k += nthreads - 2)
+        if (threadIdx.x < nthreads - 2) t.q[k] = ref_fold_candidate(sm, t.cand[k], is_end);
+      if (threadIdx.x >= nthreads - 2) {
+        const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : t.prod_g);
+        if (threadIdx.x == nthreads - 1) t.val = v;
+        else t.dotg = v;
+      }
+      for (int k = threadIdx.x; k < n; k += nthreads) t.q_plain[k] = 0.0f;  // (unused without look-ahead)
     }
+    if (threadIdx.x == 0) t.flag = la ? 1 : 0;
     __syncthreads();
   }
   if (wid == 0) {
@@ -693,7 +827,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     if (n > 0) {
       const int k = argmax_last(t.q, n);  // selectAction, Simulator.hs:202
       act = t.cand[k];
-      next_val = t.q[k];
+      next_val = t.flag ? t.q_plain[k] : t.q[k];  // (look-ahead only steers the selection: nextFrep is the real afterstate)
       const unsigned long long chg = elig_change_mask(s, act, is_end, t.n2mask);
       apply_action(sm, cell, is_end, act, chg);  // gridStep, Simulator.hs:137-144
     }

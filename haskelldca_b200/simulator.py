@@ -40,6 +40,7 @@ class Replicas:
         cfg.verify_nelig_bounds = int(opt.verify_nelig_bounds)
         cfg.trace_capacity = opt.trace
         cfg.warps_per_replica = opt.warps_per_replica
+        cfg.hoff_lookahead = int(opt.hoff_lookahead)
         cfg.call_dur, cfg.call_dur_hoff = opt.call_dur, opt.call_dur_hoff
         cfg.call_rate, cfg.hoff_prob = opt.call_rate, opt.hoff_prob
         cfg.alpha_net, cfg.alpha_avg, cfg.alpha_grad = opt.learning_rate, opt.learning_rate_avg, opt.learning_rate_grad

@@ -52,6 +52,7 @@ struct Opt {
   std::string order = "fast";   // fast | ref  (fp32 reduction order)
   std::string rng = "philox";   // philox | mt19937 (replay of the reference's stream)
   int device = 0;
+  bool hoffLookahead = false;  // extension (the reference's TODO, README.md:71-72); --order ref only
 };
 
 inline const char* usage() {
@@ -60,7 +61,8 @@ inline const char* usage() {
          "               [--hoff_prob PROBABILITY] [--n_events N] [--log_iter N] [--learning_rate F]\n"
          "               [--learning_rate_avg F] [--learning_rate_grad F] [--verify_reuse_constraint]\n"
          "               [--verify_nelig_bounds] [--backend ARG] [--min_loss F] [--fixed_rng]\n"
-         "               [--n_replicas N] [--order fast|ref] [--rng philox|mt19937] [--device N]\n\n"
+         "               [--n_replicas N] [--order fast|ref] [--rng philox|mt19937] [--device N]\n"
+         "               [--hoff_lookahead]\n\n"
          "Available options:\n"
          "  --call_dur MINUTES       Call duration for new calls. (default: 3.0)\n"
          "  --call_dur_hoff MINUTES  Call duration for handed-off calls. (default: 1.0)\n"
@@ -80,6 +82,8 @@ inline const char* usage() {
          "  --order fast|ref         fp32 reduction order (default: fast)\n"
          "  --rng philox|mt19937     random source; mt19937 replays the reference's stream (default: philox)\n"
          "  --device N               CUDA device ordinal (default: 0)\n"
+         "  --hoff_lookahead         extension: look ahead at the hand-off arrival when freeing a channel\n"
+         "                           on the END half of a hand-off (--order ref only)\n"
          "  -h,--help                Show this help text\n";
 }
 
@@ -123,6 +127,7 @@ inline Opt getOpts(int argc, const char* const* argv, uint64_t rand) {
     else if (a == "--order") o.order = need(i);
     else if (a == "--rng") o.rng = need(i);
     else if (a == "--device") o.device = (int)num("--device", need(i));
+    else if (a == "--hoff_lookahead") o.hoffLookahead = true;
     else if (a == "-h" || a == "--help") throw Error(0, usage());
     else throw Error(DCA_ERR_ARG, "Invalid option `" + a + "'\n\n" + usage());
   }
@@ -196,6 +201,7 @@ class Replicas {
     check(dca_config_defaults(&cfg), "dca_config_defaults");
     cfg.n_replicas = o.nReplicas;
     cfg.device = o.device;
+    cfg.hoff_lookahead = o.hoffLookahead ? 1 : 0;
     cfg.seed = o.rngSeed;
     cfg.rng_mode = o.rng == "philox" ? DCA_RNG_PHILOX : DCA_RNG_TAPE;
     cfg.order = o.order == "fast" ? DCA_ORDER_FAST : DCA_ORDER_REF;

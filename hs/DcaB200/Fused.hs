@@ -36,7 +36,7 @@ offNReplicas = 0; offSeed = 8; offRngMode = 24; offOrder = 28; offNEvents = 32; 
 offVerifyRC = 44; offVerifyNB = 48
 offCallDur, offCallDurHoff, offCallRate, offHoffProb, offAlphaNet, offAlphaAvg, offAlphaGrad, sizeofConfig :: Int
 offCallDur = 64; offCallDurHoff = 72; offCallRate = 80; offHoffProb = 88
-offAlphaNet = 96; offAlphaAvg = 100; offAlphaGrad = 104; sizeofConfig = 168
+offAlphaNet = 96; offAlphaAvg = 100; offAlphaGrad = 104; sizeofConfig = 176
 
 -- | every FFI return code goes through here: a failed launch (not an sm_100a device, tensor-memory allocation
 -- failure, bad handle, a replica without its random tape ...) aborts instead of leaving a status at Running

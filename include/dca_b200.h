@@ -106,6 +106,13 @@ typedef struct {
   float alpha_net, alpha_avg, alpha_grad;               /* alphaNet, alphaAvg, alphaGrad */
   const double *call_dur_v, *call_dur_hoff_v, *call_rate_v, *hoff_prob_v;
   const float *alpha_net_v, *alpha_avg_v, *alpha_grad_v;
+  /* EXTENSION -- hand-off look-ahead, the reference's only TODO (README.md:71-72); 0 = the reference's behaviour.
+   * On the END half of a hand-off (END ch (Just toCell), src/EventGen.hs:94-109) the channel to free is chosen by
+   *   q[k] = max over h eligible at toCell on afterstate_k of V(afterstate_k with h assigned at toCell)
+   * (V(afterstate_k) when none is eligible) instead of V(afterstate_k); the TD update still uses the real afterstate.
+   * Implemented by dca_run for DCA_ORDER_REF (dca_create rejects it with DCA_ORDER_FAST). */
+  int32_t hoff_lookahead;
+  int32_t reserved_;
 } dca_config;
 
 /* Event, src/Base.hs:101-105 */

@@ -451,6 +451,47 @@ int orc_get_action(int order, int r, int c, int is_end, const float *w, const ui
   return (int)chs[idx];
 }
 
+/* hand-off look-ahead (extension, see dca_oracle.h) */
+int orc_get_action_lookahead(int order, int r, int c, int hr, int hc, const float *w,
+                             const uint8_t *grid, const int64_t *frep, int64_t *next_frep,
+                             int *ncand_out, float *qvals_out) {
+  int64_t chs[CH_], hs[CH_];
+  const int n = orc_inuse_chs(grid, r, c, chs);
+  if (ncand_out) *ncand_out = n;
+  if (n == 0) {
+    memcpy(next_frep, frep, sizeof(int64_t) * ORC_FREP_SIZE);
+    return -1;
+  }
+  int64_t *afreps = (int64_t *)malloc(sizeof(int64_t) * ORC_FREP_SIZE * (size_t)n);
+  int64_t *freps2 = (int64_t *)malloc(sizeof(int64_t) * ORC_FREP_SIZE * (size_t)CH_);
+  float q[CH_];
+  orc_inc_afterstate_freps(r, c, 1, chs, n, grid, frep, afreps);
+  for (int k = 0; k < n; ++k) {
+    const int64_t *af = afreps + (size_t)k * ORC_FREP_SIZE;
+    uint8_t gk[ORC_GRID_SIZE];
+    memcpy(gk, grid, ORC_GRID_SIZE);
+    orc_execute_action(1, r, c, (int)chs[k], gk);
+    const int m = orc_eligible_chs(gk, hr, hc, hs);
+    if (m == 0) {
+      q[k] = orc_dense_dot(order, af, w);
+    } else {
+      orc_inc_afterstate_freps(hr, hc, 0, hs, m, gk, af, freps2);
+      float best = orc_dense_dot(order, freps2, w);
+      for (int j = 1; j < m; ++j) {
+        const float v = orc_dense_dot(order, freps2 + (size_t)j * ORC_FREP_SIZE, w);
+        if (v > best) best = v;
+      }
+      q[k] = best;
+    }
+  }
+  const int idx = orc_argpmax(q, n);
+  if (qvals_out) memcpy(qvals_out, q, sizeof(float) * (size_t)n);
+  memcpy(next_frep, afreps + (size_t)idx * ORC_FREP_SIZE, sizeof(int64_t) * ORC_FREP_SIZE);
+  free(afreps);
+  free(freps2);
+  return (int)chs[idx];
+}
+
 /* backward, Agent.hs:44-81 */
 float orc_backward(int order, float aN, float aA, float aG, const int64_t *frep,
                    const int64_t *next_frep, float reward, float *w, float *wg,
@@ -936,8 +977,13 @@ static int run_step(orc_sim *s, orc_trace *tr) {
   const orc_event ev = s->event;
   const int is_end = ev.etype == ORC_END;
   int ncand = 0;
-  int ch = orc_get_action(o->order, ev.r, ev.c, is_end, s->w, s->grid, s->frep, s->next_frep,
-                          &ncand); /* accFn1 :75 */
+  int ch;
+  if (o->hoff_lookahead && is_end && ev.hoff_r >= 0) /* extension: the departure half of a hand-off */
+    ch = orc_get_action_lookahead(o->order, ev.r, ev.c, ev.hoff_r, ev.hoff_c, s->w, s->grid, s->frep,
+                                  s->next_frep, &ncand, NULL);
+  else
+    ch = orc_get_action(o->order, ev.r, ev.c, is_end, s->w, s->grid, s->frep, s->next_frep,
+                        &ncand); /* accFn1 :75 */
   if (environment_step(s, ch) != 0) return ORC_HOST_ERROR; /* :78 */
   int is_nan = 0;
   int64_t reward = 0;

@@ -86,6 +86,10 @@ typedef struct {
   int32_t order;          /* ORC_ORDER_* */
   int32_t rng_mode;       /* ORC_RNG_* */
   uint64_t replica;       /* Philox stream id (ignored for MT) */
+  int32_t hoff_lookahead; /* EXTENSION (the reference's only TODO, README.md:71-72; 0 = the reference's behaviour):
+                             on the END half of a hand-off choose the channel to free by looking ahead at the HOFF
+                             arrival that follows in the target cell -- see orc_get_action_lookahead */
+  int32_t pad_;
 } orc_opt;
 
 void orc_opt_defaults(orc_opt *o);
@@ -143,6 +147,17 @@ int orc_select_action(int order, int r, int c, int is_end, const int64_t *chs, i
 int orc_get_action(int order, int r, int c, int is_end, const float *w,
                    const uint8_t *grid, const int64_t *frep, int64_t *next_frep,
                    int *ncand_out);
+/* Hand-off look-ahead (extension; README.md:71-72 names it as the reference's TODO, the reference defines nothing
+ * more).  For an event END _ (Just toCell) at (r, c) -- the departure half of a hand-off, directly followed by the
+ * HOFF arrival at toCell (EventGen.hs:94-109) -- the value of freeing the in-use channel k is not V(afterstate_k) but
+ *   q[k] = max over h eligible at toCell ON afterstate_k of V(afterstate_k with h assigned at toCell),
+ *   q[k] = V(afterstate_k) when no channel is eligible there (the hand-off will be rejected),
+ * every V a dense dot in `order` of the materialised feature representation (incAfterStateFreps applied twice); the
+ * maximum is a left fold with `>` over ascending h, the channel is argpmax over k (last maximum wins) as in selectAction.
+ * Only the SELECTION looks ahead: next_frep is afterstate_k of the chosen k, so backward (Agent.hs:44-81) is unchanged. */
+int orc_get_action_lookahead(int order, int r, int c, int hoff_r, int hoff_c, const float *w,
+                             const uint8_t *grid, const int64_t *frep, int64_t *next_frep,
+                             int *ncand_out, float *qvals_out);
 /* backward: updates w, wg, avg_reward in place; returns loss; *is_nan set */
 float orc_backward(int order, float alpha_n, float alpha_a, float alpha_g,
                    const int64_t *frep, const int64_t *next_frep, float reward,

@@ -54,6 +54,8 @@ class Opt(C.Structure):
         ("order", C.c_int32),
         ("rng_mode", C.c_int32),
         ("replica", C.c_uint64),
+        ("hoff_lookahead", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 
@@ -120,6 +122,7 @@ def lib():
             "orc_argpmax": (i32, [vp, i32]),
             "orc_select_action": (i32, [i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
             "orc_get_action": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp]),
+            "orc_get_action_lookahead": (i32, [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
             "orc_backward": (f32, [i32, f32, f32, f32, vp, vp, f32, vp, vp, vp, vp]),
             "orc_grid_step_train": (f32, [i32, f32, f32, f32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
             "orc_rng_create": (vp, [i32, u64, u64]),
@@ -327,6 +330,16 @@ def get_action(order, cell, is_end, w, grid, frep):
         C.byref(ncand),
     )
     return ch, nf, ncand.value
+
+
+def get_action_lookahead(order, cell, hoff_cell, w, grid, frep):
+    """hand-off look-ahead (extension): -> (ch, next_frep, ncand, q[ncand])"""
+    nf = np.zeros((ROWS, COLS, NFEATS), dtype=np.int64)
+    ncand = C.c_int()
+    q = np.zeros(CHANNELS, dtype=np.float32)
+    ch = lib().orc_get_action_lookahead(order, cell[0], cell[1], hoff_cell[0], hoff_cell[1], _p(_f32(w)), _p(_grid(grid)),
+                                        _p(_frep(frep)), _p(nf), C.byref(ncand), _p(q))
+    return ch, nf, ncand.value, q[: ncand.value].copy()
 
 
 def backward(order, aN, aA, aG, frep, next_frep, reward, w, wg, avg_reward):

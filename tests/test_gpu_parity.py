@@ -456,3 +456,33 @@ def test_guard_rails_of_the_c_abi():
             s = sims.read_summary()
             assert s["status"][0] == _ffi.RUNNING and s["status"][1] == _ffi.QUEUE_OVERFLOW, s["status"]
             assert sims.sum_stats()[0][9] == 1
+
+
+@pytest.mark.parametrize("rng,kw", [("philox", dict(hoff_prob=0.3)), ("mt19937", dict(hoff_prob=0.15, call_dur_hoff=1.0)),
+                                    ("philox", dict(hoff_prob=0.6, call_rate=400.0, call_dur=1.0))])
+def test_handoff_lookahead_matches_the_oracle(rng, kw):
+    """The extension (the reference's TODO, README.md:71-72; include/dca_b200.h dca_config.hoff_lookahead) in the
+    REF-order run kernel against the oracle's first-principles definition: every event bit for bit."""
+    from haskelldca_b200 import Opt, Replicas
+    from haskelldca_b200._ffi import DcaError
+
+    n_rep, n_ev = (3, 4000) if rng == "philox" else (1, 6000)
+    orng = po.RNG_PHILOX if rng == "philox" else po.RNG_MT
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="ref", rng=rng, rng_seed=0 if rng == "mt19937" else 12,
+                      hoff_lookahead=True, trace=n_ev, **kw)) as sims:
+        sims.run(n_ev)
+        for r in range(n_rep):
+            o = po.Sim(po.default_opt(order=po.ORDER_REF, rng_mode=orng, seed=0 if rng == "mt19937" else 12, replica=r, n_events=n_ev,
+                                      hoff_lookahead=1, **kw))
+            status, done, tr = o.run(n_ev, trace=True)
+            assert sims.read_status(r)[0] == status and done == n_ev
+            assert_trace_equal(sims.read_trace(r), tr)
+            assert_state_equal(sims.read_state(r), o.read())
+            # the look-ahead did steer some decisions: the plain run of the same stream differs
+            if r == 0:
+                p = po.Sim(po.default_opt(order=po.ORDER_REF, rng_mode=orng, seed=0 if rng == "mt19937" else 12, replica=r,
+                                          n_events=n_ev, **kw))
+                _, _, trp = p.run(n_ev, trace=True)
+                assert not np.array_equal(trp["ch"], tr["ch"])
+    with pytest.raises(DcaError):  # the FAST kernel has no look-ahead path
+        Replicas(Opt(n_events=10, order="fast", hoff_lookahead=True))

@@ -110,3 +110,32 @@ def test_haskell_bindings_match_the_library():
     for hs_name, field in want.items():
         assert offs[hs_name] == getattr(_ffi.Config, field).offset, hs_name
     assert offs["sizeofConfig"] == C.sizeof(_ffi.Config)
+
+
+def test_haskell_patch_applies(tmp_path):
+    """hs/patches/0001-backend-gpu.patch is a real unified diff against the reference modules: it must apply cleanly
+    (`patch -p1`) to a copy of the files it names.  Needs the reference tree (absent on the GPU box: skipped there)."""
+    import shutil
+    import subprocess
+
+    ref = "/root/reference"
+    patch = os.path.join(ROOT, "hs", "patches", "0001-backend-gpu.patch")
+    files = ["src/Base.hs", "src/Opt.hs", "src/AccUtils.hs", "src/SimRunner.hs", "dca.cabal"]
+    if not all(os.path.exists(os.path.join(ref, f)) for f in files) or not shutil.which("patch"):
+        pytest.skip("reference tree or patch(1) not available")
+    for f in files:
+        dst = tmp_path / f
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        shutil.copy(os.path.join(ref, f), dst)
+    r = subprocess.run(["patch", "-p1", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "| GPU" in (tmp_path / "src/Base.hs").read_text()
+    sim = (tmp_path / "src/SimRunner.hs").read_text()
+    assert "gpuGetAction RefOrder" in sim and "runSimGpu" in sim and "runN bkend getAction" in sim
+    opt = (tmp_path / "src/Opt.hs").read_text()
+    assert '"gpu" -> return GPU' in opt and "n_replicas" in opt
+    # the modules the patch imports exist and export what it uses
+    backend = open(os.path.join(ROOT, "hs", "DcaB200", "Backend.hs")).read()
+    fused = open(os.path.join(ROOT, "hs", "DcaB200", "Fused.hs")).read()
+    assert "gpuGetAction" in backend and "gpuGridStepTrain" in backend and "GpuOrder(..)" in backend
+    assert "module DcaB200.Fused (runSimGpu, RngSource(..)" in fused
