@@ -168,6 +168,43 @@ def oracle_spot_check(sims, first, n_rep, n_ev, hoff_prob):
     return True, [first + x for x in spot], None
 
 
+def inlib_allreduce_check(n_dev):
+    """dca_allreduce_stats (the in-library NCCL path: one process, one handle per device, ncclCommInitAll) on the first
+    min(n_dev, 4) devices of the box: its int64[10] must equal the sum of the per-device dca_sum_stats and the counters
+    of the same replicas run on ONE device.  Never raises: the outcome is reported in checks."""
+    try:
+        import numpy as np
+
+        from haskelldca_b200 import Opt, Replicas, _ffi, allreduce_stats
+
+        n_dev = min(n_dev, _ffi.load().dca_device_count(), 4)
+        if n_dev < 2:
+            return {"ran": False, "why": "needs two CUDA devices"}
+        n_rep, n_ev = 64, 500
+        sets, totals = [], []
+        try:
+            for d in range(n_dev):
+                s = Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=4, device=d,
+                                 first_replica=d * n_rep, hoff_prob=0.1))
+                s.run(n_ev)
+                sets.append(s)
+                totals.append(s.sum_stats()[0])
+            out = allreduce_stats(sets)
+            again = allreduce_stats(sets)  # the cached communicators serve a second call
+        finally:
+            for s in sets:
+                s.close()
+        with Replicas(Opt(n_replicas=n_dev * n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=4, hoff_prob=0.1)) as one:
+            one.run(n_ev)
+            single = one.sum_stats()[0]
+        ok = bool(np.array_equal(out, sum(totals)) and np.array_equal(out, single) and np.array_equal(out, again)
+                  and out[8] == n_dev * n_rep * n_ev and out[9] == 0)
+        return {"ran": True, "ok": ok, "devices": n_dev, "events": int(out[8]),
+                "what": "dca_allreduce_stats == sum of per-device dca_sum_stats == the same replicas on one device"}
+    except Exception as e:  # noqa: BLE001
+        return {"ran": True, "ok": False, "error": repr(e)[:300]}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's algorithm on the host cores.  haskelldca is Haskell/Accelerate
     (no GHC, no LLVM 6 here), so this arm runs the oracle port in the reference's own arithmetic
@@ -214,6 +251,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-spot-check", action="store_true", help="skip the oracle spot check of the timed configuration")
+    ap.add_argument("--no-inlib-allreduce", action="store_true", dest="no_inlib_allreduce",
+                    help="N > 1: skip the check of dca_allreduce_stats (in-library NCCL, one process over several devices)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -233,6 +272,9 @@ def main():
     _ffi.load(build_if_missing=False)  # the prebuilt sm_100a library, or fail
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    # the in-library NCCL reduction (single process, several devices) is exercised by rank 0 before it joins the
+    # process group -- the other ranks are still in the rendezvous and hold no kernels on their devices
+    inlib = inlib_allreduce_check(world) if (world > 1 and rank == 0 and not args.no_inlib_allreduce) else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -397,7 +439,9 @@ def main():
             "clocks": clocks,
             "checks": {"all_replicas_success": bool(ok_local), "blocking_probability": bp, "events_per_step": events_all,
                        "wall_ms_per_step": wall_ms_max / args.steps,
-                       "oracle_spot_check": spot["ok"] if spot else None, "oracle_spot_check_detail": spot},
+                       "oracle_spot_check": spot["ok"] if spot else None, "oracle_spot_check_detail": spot,
+                       "nccl_stats_allreduce": {"torch_distributed_ranks": world, "summed_events": events_all,
+                                                "in_library_dca_allreduce_stats": inlib}},
         }
         if not args.no_cpu_baseline and world == 1:
             import pyoracle as po
