@@ -175,6 +175,7 @@ struct dca_handle {
   HostView* d_view = nullptr;
   StepOut* d_stepout = nullptr;
   float* d_agents = nullptr;  // dca_read_agents: [2][chunk][3479] + [chunk] floats, allocated at first use
+  unsigned* d_units = nullptr;  // FAST run kernel: chunks of replica r done in the current launch
   std::string err;
   float last_ms = 0.f;
   long long launches = 0;
@@ -273,6 +274,13 @@ int launch_init(dca_handle* h, int only_replica) {
 
 bool bad_replica(const dca_handle* h, int r) { return !h || r < 0 || r >= h->n; }
 
+// events per unit of the FAST run kernel (see k_run_fast): small enough that the launch ends within a fraction of a
+// per cent of the ideal time, large enough that staging a replica in and out (100 KB) is noise
+#ifndef DCA_FAST_CHUNK_EVENTS
+#define DCA_FAST_CHUNK_EVENTS 4096
+#endif
+constexpr long long kFastChunkEvents = DCA_FAST_CHUNK_EVENTS;
+
 template <typename K>
 int set_smem(dca_handle* h, K kernel, size_t bytes = sizeof(Smem)) {
   CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -324,6 +332,7 @@ int dca_destroy(dca_handle* h) {
   cudaFree(h->d_a_net); cudaFree(h->d_a_avg); cudaFree(h->d_a_grad);
   cudaFree(h->d_tape_w); cudaFree(h->d_tape_l); cudaFree(h->d_tape_off);
   cudaFree(h->d_agents);
+  cudaFree(h->d_units);
   cudaFree(h->d_trace); cudaFree(h->d_sum); cudaFree(h->d_summary); cudaFree(h->d_view); cudaFree(h->d_stepout);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -411,6 +420,7 @@ int dca_create(const dca_config* cfg, dca_handle** out) {
       (rc = set_smem(h, k_run<ORDER_REF, false>)) || (rc = set_smem(h, k_run<ORDER_REF, true>)) ||
       (rc = set_smem(h, k_step<ORDER_REF>)) || (rc = set_smem(h, k_gf_violates)))
     return bail(rc);
+  CKB(cudaMalloc(&h->d_units, sizeof(unsigned) * (size_t)h->n));
   if ((rc = dca_reset(h))) return bail(rc);
   *out = h;
   return DCA_OK;
@@ -513,8 +523,16 @@ int dca_run(dca_handle* h, int64_t max_events) {
   const size_t smem = sizeof(Smem);
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->cfg.order == DCA_ORDER_FAST) {
-    if (trace_fast) fast::k_run_fast<true><<<grid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
-    else fast::k_run_fast<false><<<grid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
+    // one CTA per unit (replica, chunk of kFastChunkEvents events), numbered chunk-major
+    a.chunk_events = kFastChunkEvents;
+    const long long chunks = std::max<long long>(1, (max_events + kFastChunkEvents - 1) / kFastChunkEvents);
+    if (chunks * (long long)h->n > 0x7fffffffLL) return fail(h, DCA_ERR_ARG, "dca_run: max_events x n_replicas too large for one launch");
+    a.n_chunks = (unsigned)chunks;
+    a.chunk_done = h->d_units;
+    CK(cudaMemsetAsync(h->d_units, 0, sizeof(unsigned) * (size_t)h->n, h->stream));
+    const dim3 fgrid((unsigned)(chunks * (long long)h->n));
+    if (trace_fast) fast::k_run_fast<true><<<fgrid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
+    else fast::k_run_fast<false><<<fgrid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
   } else {
     if (trace) k_run<ORDER_REF, true><<<grid, block, smem, h->stream>>>(a);
     else k_run<ORDER_REF, false><<<grid, block, smem, h->stream>>>(a);

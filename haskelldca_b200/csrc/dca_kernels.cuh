@@ -37,6 +37,10 @@ struct RunArgs {
   TraceRec* trace;                  // [n_replicas][trace_cap] or null
   int trace_cap;
   int lookahead;                    // hand-off look-ahead (extension; REF-order kernel only)
+  // FAST kernel: the launch is cut into units (replica, chunk of chunk_events events), one CTA each -- see k_run_fast
+  unsigned* chunk_done;             // [n_replicas]: chunks of the replica completed in this launch (zeroed before the launch)
+  long long chunk_events;
+  unsigned n_chunks;
 };
 
 constexpr int LA_PAIRS = 1008;  // 8 rounds of 126 folding threads

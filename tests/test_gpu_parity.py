@@ -486,3 +486,29 @@ def test_handoff_lookahead_matches_the_oracle(rng, kw):
                 assert not np.array_equal(trp["ch"], tr["ch"])
     with pytest.raises(DcaError):  # the FAST kernel has no look-ahead path
         Replicas(Opt(n_events=10, order="fast", hoff_lookahead=True))
+
+
+def test_units_of_a_launch_chain_correctly():
+    """dca_run (FAST order) cuts a launch into units of 4096 events per replica, one CTA each, chained through a
+    release / acquire counter: a replica that stops in its first unit is skipped by its later ones, a launch whose
+    length is not a multiple of the unit equals the oracle, and very many short units keep their order."""
+    from haskelldca_b200 import Opt, Replicas, _ffi
+
+    with Replicas(Opt(n_replicas=3, n_events=100000, min_loss=1e9, order="fast")) as sims:  # ZeroLoss at event 51
+        sims.run(50000)  # 13 units per replica
+        s = sims.read_summary()
+        assert (s["status"] == _ffi.ZERO_LOSS).all() and (s["iter"] == 51).all()
+    n = 4096 * 3 + 77
+    o, status, tr = oracle_run(po.ORDER_FAST, n, seed=21, hoff=0.15, rng=po.RNG_PHILOX, replica=9)
+    with Replicas(Opt(n_replicas=1, n_events=n, order="fast", rng="philox", rng_seed=21, hoff_prob=0.15, first_replica=9, trace=n)) as sims:
+        sims.run(n)
+        assert sims.read_status(0)[0] == status == po.SUCCESS
+        assert_trace_equal(sims.read_trace(0), tr)
+        assert_state_equal(sims.read_state(0), o.read())
+    # one replica, 40 units in a single launch: every unit waits for its predecessor
+    n = 4096 * 40
+    o = po.FastSim(po.default_opt(rng_mode=po.RNG_PHILOX, seed=5, replica=0, n_events=n))
+    o.run(n)
+    with Replicas(Opt(n_replicas=1, n_events=n, order="fast", rng="philox", rng_seed=5)) as sims:
+        sims.run(n)
+        assert_state_equal(sims.read_state(0), o.read())
