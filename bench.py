@@ -43,10 +43,18 @@ def kernel_ceilings():
         return None
 
 
-def measured_traffic():
-    """DRAM bytes of one k_run_fast launch on the bench workload (dram__bytes_read.sum + dram__bytes_write.sum of
-    `ncu --set full`; one state blob in and out per replica, whatever the number of events per launch)."""
+def measured_traffic(n_rep=None, n_ev=None):
+    """DRAM bytes of one k_run_fast launch on the bench workload, from the committed ncu capture (dram__bytes_read.sum +
+    dram__bytes_write.sum of `ncu --set full`).  A launch stages every replica's state in and out once per UNIT of
+    dca_run_unit_events() events; the capture measures launches of one unit per replica, so the bench launch's traffic
+    is the captured bytes per unit x the units it runs."""
     c = kernel_ceilings()
+    if c and c.get("dram_bytes_per_unit") and n_rep and n_ev:
+        from haskelldca_b200 import _ffi
+
+        unit = int(_ffi.load().dca_run_unit_events())
+        units = n_rep * -(-n_ev // unit)
+        return float(c["dram_bytes_per_unit"]) * units, f"{c['dram_bytes_per_unit']:.0f} B per unit x {units} units of {unit} events; " + c.get("source", "")
     if c and c.get("dram_bytes_per_launch"):
         return float(c["dram_bytes_per_launch"]), c.get("source", "")
     try:
@@ -401,7 +409,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        traffic, traffic_src = measured_traffic()
+        traffic, traffic_src = measured_traffic(n_rep, n_ev)
         ceil = kernel_ceilings()
         binding = None
         if ceil:
@@ -432,7 +440,7 @@ def main():
                          "note": "achieved = events/s/GPU x 55 664 algorithmic bytes (r+w of wNet, wGradCorr per event, Agent.hs:67-76) over the "
                                  "kernel's own CUDA-event duration, against the measured HBM peak as SURVEY.md 8(d) defines the fraction.  The "
                                  "kernel keeps a replica's weights on chip (shared memory + tensor memory) for the whole launch, so real DRAM "
-                                 "traffic (`traffic`) is one state blob in and out per replica per launch and frac > 1 is multi-event residency, "
+                                 "traffic (`traffic`) is one state blob in and out per replica per unit of 4096 events and frac > 1 is multi-event residency, "
                                  "not bandwidth; what binds is in `binding_ceilings` (ncu: issue slots, the shared-memory data pipe, stalls)"},
             "e2e": e2e,
             "gpu_launches": int(launches),

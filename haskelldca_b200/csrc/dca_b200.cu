@@ -545,6 +545,8 @@ int dca_run(dca_handle* h, int64_t max_events) {
   return DCA_OK;
 }
 
+int64_t dca_run_unit_events(void) { return kFastChunkEvents; }
+
 int dca_elapsed_ms(const dca_handle* h, float* ms) {
   if (!h || !ms) return DCA_ERR_ARG;
   *ms = h->last_ms;

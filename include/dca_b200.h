@@ -173,6 +173,10 @@ int dca_set_rng_mt19937(dca_handle *h, int32_t replica, uint64_t seed, size_t n_
  * (getAction -> environmentStep -> gridStepTrain each) on the device, stopping
  * early with its own SimStop status.  Returns when the device is done. */
 int dca_run(dca_handle *h, int64_t max_events);
+/* DCA_ORDER_FAST: dca_run cuts a launch into units of this many events per replica (one CTA each, chained in
+ * order), so that the device stays evenly loaded to the end of the launch; a replica's state is staged from / to
+ * HBM once per unit.  Results do not depend on it. */
+int64_t dca_run_unit_events(void);
 /* device time of the last dca_run / dca_reset (CUDA events on the launch stream) */
 int dca_elapsed_ms(const dca_handle *h, float *ms);
 int dca_last_launch_count(const dca_handle *h, int64_t *n_kernels);

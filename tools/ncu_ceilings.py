@@ -44,6 +44,13 @@ res = {
     "source": f"ncu --set full --clock-control none --import-source on -k regex:k_run_fast -s 1 -c 1 python tools/prof_run.py 4096 2000 20000 ({rep.split('/')[-1]})",
 }
 res["dram_bytes_per_launch"] = res["dram_bytes_read"] + res["dram_bytes_write"]
+# the profiled launch runs ONE unit (replica, <= 4096 events) per CTA: a replica's state is staged in and out once per unit
+try:
+    n_units = int(str(res["grid"]).strip("()").split(",")[0])
+    res["units_in_launch"] = n_units
+    res["dram_bytes_per_unit"] = res["dram_bytes_per_launch"] / n_units
+except Exception:
+    pass
 print(json.dumps(res, indent=1))
 if out_path:
     json.dump(res, open(out_path, "w"), indent=1)
