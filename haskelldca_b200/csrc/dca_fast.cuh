@@ -93,10 +93,13 @@ struct alignas(16) SmemF {
   float P[72];              // plane sums of x.w (current state, current weights)
   float q[72];              // afterstate values of the candidates
   float Wg[4];              // per-warp partial sums of x.wGradCorr
+  // the decision of the current event, published by agent warp 0 for the event warp (which then needs no argmax of
+  // its own): the chosen channel (-1 = Nothing), the TD error, and -- for the trace -- avgReward and the calls in progress
+  struct alignas(16) Pub { int act; float tderr; float avg_reward; int ncalls; } pub;
   float alpha_net, alpha_avg, alpha_grad;  // alphaNet, alphaAvg, alphaGrad of this replica
   int status;
   uint32_t tmem_base;       // tensor-memory columns of this CTA (wGradCorr, DCA_WG_TMEM)
-  float v_pub;              // V(s) of the current event, published by the agents before the argmax barrier
+  float v_pub;              // (step kernel only)
   uint32_t pad_[2];
   uint2 n4rows[NCELL];      // per cell: byte r = the 7 column bits of row r of N4(cell) \ {cell} ...
   uint2 n2rows[NCELL];      // ... and of N2(cell) u {cell}  (copied from the constant tables: a shared-memory load
@@ -113,13 +116,14 @@ __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0, 128;" 
 // The per-event synchronisation of the run kernel is producer / consumer, so that neither side waits for the other
 // where it does not need its data:
 //   barrier 2 (96):  the agents among themselves -- every candidate's value is in sm.q
-//   barrier 3 (128): the same fact for the event warp: the agents arrive (and go on), the event warp waits
+//   barrier 3 (64):  the decision (sm.pub) is published: agent warp 0 arrives right after its argmax, the event warp waits
 //   barrier 4 (128): the next event's record (kind, cell, masks, candidates) and the stop status are published and the
 //                    plane sums of the dense pass are complete: the event warp arrives (and runs on to the next
 //                    event's queue work), the agents wait
 //   barrier 5 (128): TRACE instantiation only -- the afterstate is complete (the event warp hashes / verifies it)
-__device__ __forceinline__ void agents_q_ready() { asm volatile("bar.arrive 3, 128;\n\tbar.sync 2, 96;" ::: "memory"); }
-__device__ __forceinline__ void event_wait_q() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
+__device__ __forceinline__ void agents_q_ready() { asm volatile("bar.sync 2, 96;" ::: "memory"); }
+__device__ __forceinline__ void decision_published() { asm volatile("bar.arrive 3, 64;" ::: "memory"); }
+__device__ __forceinline__ void event_wait_decision() { asm volatile("bar.sync 3, 64;" ::: "memory"); }
 __device__ __forceinline__ void event_publish_next() { asm volatile("bar.arrive 4, 128;" ::: "memory"); }
 __device__ __forceinline__ void agents_wait_next() { asm volatile("bar.sync 4, 128;" ::: "memory"); }
 __device__ __forceinline__ void agents_afterstate_done() { asm volatile("bar.arrive 5, 128;" ::: "memory"); }
@@ -706,16 +710,20 @@ __device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const 
 // ---------------------------------------------------------------------------
 // Event side (warp 3).  All registers are warp-uniform unless noted.
 // ---------------------------------------------------------------------------
+// (The event warp's chain is the most expensive place for an instruction -- one more per event costs ~0.07 % of the
+//  kernel's throughput, twice what it costs on an agent warp -- so everything it counts per event is a 32-bit delta
+//  of this unit, folded into the 64-bit values of the replica blob when the unit ends.)
 struct EvRegs {
   unsigned n_end, next_id;
-  unsigned long long ndraws;
-  long long iter, n_events, loss_n;
+  int left_success;                     // events until iter == nEvents (clamped to int: a unit is far shorter)
+  int left_50;                          // events until iter > 50 can hold (the ZeroLoss rule, SimRunner.hs:161)
   float loss_sum, min_loss;
   double mean_new, call_dur, call_dur_hoff;
   unsigned long long hoff_thresh;       // p < hoffProb  <=>  (word >> 11) < ceil(hoffProb * 2^53)   (p = (word >> 11) * 2^-53 exactly)
-  long long stats[8];                   // Stats counters (src/Stats.hs:15-30)
+  unsigned stats[8];                    // Stats counters (src/Stats.hs:15-30): increments of this unit
   int dirty1;                           // a second queue block whose minimum must be re-scanned after a pop (-1 = none; rare)
   unsigned long long dbase;             // cached draws: lane l holds draw dbase + l ...
+  unsigned dpos;                        // ... draws dbase .. dbase + dpos - 1 are consumed (the replica's draw count is dbase + dpos)
   unsigned long long dword;             // ... its random word (per lane)
   double dnl;                           // ... and -log(u) of that word (per lane)
   // random source
@@ -761,22 +769,23 @@ __device__ __noinline__ Draw ev_refill(int rng_mode, uint32_t k0, uint32_t k1, u
   }
   return r;
 }
-// make sure draws ndraws .. ndraws + 3 are cached
+// make sure the next four draws are cached
 __device__ __forceinline__ void ev_draws(EvRegs& e) {
-  if (e.ndraws >= e.dbase && e.ndraws + 4 <= e.dbase + 32) return;  // warp-uniform
-  e.dbase = e.ndraws;
+  if (e.dpos + 4 <= 32) return;  // warp-uniform
+  e.dbase += e.dpos;
+  e.dpos = 0;
   const Draw r = ev_refill(e.rng_mode, e.k0, e.k1, e.stream, e.tape_w, e.tape_l, e.tape_len, e.dbase);
   e.dword = r.word;
   e.dnl = r.nl;
 }
-// draw ndraws + k: its word / its -log(u)   (k < 4 is always cached after ev_draws)
+// the k-th draw from now: its word / its -log(u)   (k < 4 is always cached after ev_draws)
 __device__ __forceinline__ unsigned long long ev_draw_word(const EvRegs& e, unsigned k) {
-  const unsigned long long i = e.ndraws + k - e.dbase;
+  const unsigned i = e.dpos + k;
   const unsigned long long w = __shfl_sync(0xffffffffu, e.dword, (int)(i & 31));
-  return i < 32 ? w : ev_word(e, e.ndraws + k);
+  return i < 32 ? w : ev_word(e, e.dbase + i);
 }
 __device__ __forceinline__ double ev_draw_nl(const EvRegs& e, unsigned k) {
-  return __shfl_sync(0xffffffffu, e.dnl, (int)((e.ndraws + k - e.dbase) & 31));
+  return __shfl_sync(0xffffffffu, e.dnl, (int)((e.dpos + k) & 31));
 }
 
 // candidate channels of event `ev` (getAction, Simulator.hs:161-165), ascending
@@ -980,7 +989,7 @@ __device__ __forceinline__ int ev_env_push(SmemF& sm, EvRegs& e, QBlk& qb, const
           ++used;
           z = (int)(wz & 0xFFULL);
           if (z >= n_reject) break;
-          if (e.rng_mode == RNG_TAPE && e.ndraws + used >= e.tape_len) break;  // exhausted tape: stop is flagged
+          if (e.rng_mode == RNG_TAPE && e.dbase + e.dpos + used >= e.tape_len) break;  // exhausted tape: stop is flagged
         }
         end_hoff = c_tab.n2list[cell][z % m];
       }
@@ -989,14 +998,14 @@ __device__ __forceinline__ int ev_env_push(SmemF& sm, EvRegs& e, QBlk& qb, const
       if (end_hoff != HOFF_NONE) e.next_id++;  // the HOFF event's id (pushed right after its END, never stored)
       have_end = true;
     }
-    e.ndraws += used;
+    e.dpos += used;
   } else if (type == EV_HOFF) {
     if (accepted) {  // generateHoffEndEvent, EventGen.hs:114-116
       const double te = __dadd_rn(time, __dmul_rn(ev_draw_nl(e, 0), e.call_dur_hoff));
       t_end = (unsigned long long)__double_as_longlong(te);
       id_end = e.next_id++;
       have_end = true;
-      e.ndraws += 1;
+      e.dpos += 1;
     }
   }
   // the queue writes: NEW at slot `cell`, END (cell, <channel pending>) [hoff] at slot QNEW + n_end -- by lane 0 (the only
@@ -1055,8 +1064,8 @@ __device__ __forceinline__ EnvNext ev_env_pop(SmemF& sm, EvRegs& e, QBlk& qb, co
     const unsigned slot = q_min_slot(qb);
     const unsigned b = slot >> 5, i = 32 * b + (unsigned)lane;
     nx.time = sm.q_time[slot];
-    const int key = sm.q_key[slot < (unsigned)QCAP ? slot : 0];
-    const int hoff = sm.q_hoff[slot < (unsigned)QCAP ? slot : 0];
+    const int key = sm.q_key[slot];    // (slot is a live one: < QNEW + n_end <= QCAP)
+    const int hoff = sm.q_hoff[slot];
     unsigned long long bt = (unsigned long long)__double_as_longlong(sm.q_time[i]);
     unsigned bid = sm.q_id[i];
     if (slot < QNEW) {
@@ -1317,8 +1326,12 @@ __device__ __forceinline__ void store_wg(const Agent& ag, RepState* g, const Lan
 }
 
 __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepState* g, int rep) {
-  e.n_end = g->n_end; e.next_id = g->next_id; e.ndraws = g->ndraws;
-  e.iter = g->iter; e.n_events = g->n_events; e.loss_n = g->loss_n;
+  e.n_end = g->n_end; e.next_id = g->next_id;
+  {
+    const long long iter = g->iter, to_go = g->n_events - iter, to_50 = 50 - iter;
+    e.left_success = to_go > 0x7fffffffLL ? 0x7fffffff : (to_go < 0 ? -1 : (int)to_go);  // (<= 0: the rule never fires again)
+    e.left_50 = to_50 < 0 ? 0 : (int)to_50;
+  }
   e.loss_sum = g->loss_sum; e.min_loss = g->min_loss;
   e.mean_new = g->mean_new; e.call_dur = g->call_dur; e.call_dur_hoff = g->call_dur_hoff;
   {  // hoffProb as an integer threshold on the 53 random bits (exact: scaling by 2^53 and ceil are)
@@ -1326,9 +1339,9 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
     e.hoff_thresh = !(h > 0.0) ? 0ULL : (h >= 1.0 ? (1ULL << 53) : (unsigned long long)ceil(h * 9007199254740992.0));
   }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) e.stats[k] = g->stats[k];
+  for (int k = 0; k < 8; ++k) e.stats[k] = 0;
   e.dirty1 = -1;
-  e.dbase = 0xFFFFFFFFFFFFFFF0ULL; e.dword = 0; e.dnl = 0.0;  // (empty draw cache)
+  e.dbase = g->ndraws - 32ULL; e.dpos = 32; e.dword = 0; e.dnl = 0.0;  // (empty draw cache: the first use refills it)
   e.rng_mode = a.rng_mode; e.k0 = a.key0; e.k1 = a.key1; e.stream = g->stream;
   e.tape_w = nullptr; e.tape_l = nullptr; e.tape_len = 0;
   if (a.rng_mode == RNG_TAPE && a.tape_off) {
@@ -1374,11 +1387,14 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
     const VTree vt = q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r);
     dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
-    if (l.vw == 0 && lane_id() == 0) sm.v_pub = vt.val;
     DCA_CLK(c1);
     agents_q_ready();  // B2
     DCA_CLKB(c2);
     const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
+    if (l.vw == 0) {  // warp-uniform: the event warp takes the decision from here
+      if (lane_id() == 0) *reinterpret_cast<int4*>(&sm.pub) = make_int4(d.act, __float_as_int(d.tderr), __float_as_int(avgR), ncalls);
+      decision_published();
+    }
     DCA_CLK(c3);
     // accFn2 (gridStepTrain, SimRunner.hs:100-118): afterstate + dense update + the next event's sums
     dense_pass<true, true>(sm, ag, l, d.act, is_end, d.td, n4b_r, n2b_r);
@@ -1407,10 +1423,12 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   constexpr bool sync_end = TRACE;  // (the host launches the TRACE instantiation whenever a verify flag is set)
   const int lane = lane_id();
   stage_in(sm, g);
-  float avgR = g->avg_reward;
-  int ncalls = g->ncalls;
+  float avgR = 0.0f;  // (trace only: taken from the published decision)
+  int ncalls = 0;
   EvRegs e;
   ev_load(e, a, g, rep);
+  const long long iter0 = TRACE ? g->iter : 0;  // (the trace is indexed by the replica's iteration count)
+  (void)iter0;
   cta_barrier();
   QBlk qb;
   q_build(sm, qb, e.n_end);
@@ -1444,9 +1462,6 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const double time = ev.time;
     const bool is_end = type == EV_END;
     DCA_CLK(c0);
-    // (this warp needs V(s) only for the TD error it logs and tests: the agents publish it; the TD scalars
-    //  of the weight update are not needed here)
-    const DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
     // Ahead of the agents (they may still be in the previous event's dense pass): the pop of the next event -- it
     // does not depend on WHICH channel is chosen, and this event's new events are in the queue already.  Its kind
     // and cell go to the next event record (nobody reads that one before barrier 4).
@@ -1454,12 +1469,15 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     const EnvNext en = ev_env_pop(sm, e, qb, type, ev_hoff, time, pend_slot);   // Simulator.hs:132-134: pop
     if (lane == 0) { nx.type = en.type; nx.cell = en.cell; }
     DCA_CLK(c1);
-    event_wait_q();  // B2: the agents have evaluated the candidates
+    event_wait_decision();  // agent warp 0 has published the decision of this event
     DCA_CLKB(c2);
-    VTree vt;
-    vt.val = sm.v_pub;
-    vt.dotg = 0.0f;
-    const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
+    struct { int act; float tderr; } d;
+    {
+      const int4 p = *reinterpret_cast<const int4*>(&sm.pub);
+      d.act = p.x;
+      d.tderr = __int_as_float(p.y);
+      if (TRACE) { avgR = __int_as_float(p.z); ncalls = p.w; }
+    }
     DCA_CLK(c3);
     if (lane == 0 && d.act >= 0) sm.grid[cell][d.act >> 5] ^= 1u << (d.act & 31);  // executeAction, Gridfuncs.hs:105-110
     ev_env_post<false>(sm, nx, en, type, cell, ev_ch, d.act, e.n_end);       // the channel-dependent rest
@@ -1476,14 +1494,11 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     DCA_CLKB(s3);
     const int n_next = agent_candidates(sm, nx, en.type, en.cell);
     DCA_CLK(s4);
-    e.iter += 1;  // Simulator.hs:131
+    // ssIter += 1 (Simulator.hs:131): the replica's iteration count is iter0 + it + 1 from here on
     // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
     int stop = ST_RUNNING;
     if (d.tderr != d.tderr) stop = ST_NAN_LOSS;
-    else {
-      e.loss_sum = __fadd_rn(e.loss_sum, d.tderr);
-      e.loss_n += 1;
-    }
+    else e.loss_sum = __fadd_rn(e.loss_sum, d.tderr);  // (the number of losses: every event of the unit but a NaN one)
     if (stop == ST_RUNNING && overflow_now) stop = ST_QUEUE_OVERFLOW;
     if (sync_end) {
       event_wait_afterstate();  // the agents have moved frep to the afterstate
@@ -1491,11 +1506,11 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
         const int v = ev_verify(sm, a.verify_rc, a.verify_nb);
         if (v) stop = v;
       }
-      if (TRACE && a.trace && e.iter - 1 < a.trace_cap) {
+      if (TRACE && a.trace && iter0 + it < a.trace_cap) {
         unsigned long long hg, hf;
         ev_hashes(sm, hg, hf);
         if (lane == 0) {
-          TraceRec& tr = a.trace[(size_t)rep * a.trace_cap + (e.iter - 1)];
+          TraceRec& tr = a.trace[(size_t)rep * a.trace_cap + (iter0 + it)];
           tr.time = time;
           tr.loss = d.tderr;
           tr.avg_reward = avgR;
@@ -1511,9 +1526,9 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
         }
       }
     }
-    if (stop == ST_RUNNING && e.min_loss > 0.0f && e.iter > 50 && fabsf(d.tderr) < e.min_loss) stop = ST_ZERO_LOSS;
-    if (stop == ST_RUNNING && e.iter == e.n_events) stop = ST_SUCCESS;
-    if (stop == ST_RUNNING && e.rng_mode == RNG_TAPE && e.ndraws + 8 > e.tape_len) stop = ST_TAPE_EXHAUSTED;
+    if (stop == ST_RUNNING && e.min_loss > 0.0f && it + 1 > e.left_50 && fabsf(d.tderr) < e.min_loss) stop = ST_ZERO_LOSS;
+    if (stop == ST_RUNNING && it + 1 == e.left_success) stop = ST_SUCCESS;
+    if (stop == ST_RUNNING && e.rng_mode == RNG_TAPE && e.dbase + e.dpos + 8 > e.tape_len) stop = ST_TAPE_EXHAUSTED;
     if (lane == 0) sm.status = stop;
     DCA_CLK(s5);
     event_publish_next();  // B1 (non-blocking): the next event's record and the status are published
@@ -1527,8 +1542,9 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     DCA_CLK(c5);
     DCA_ACC(0, c0, c1); DCA_ACC(1, c1, c2); DCA_ACC(2, c2, c3); DCA_ACC(3, c3, c4); DCA_ACC(4, c4, c5); DCA_ACC(5, c0, c5);
     DCA_SUB(0, c3, s0); DCA_SUB(1, s0, s1); DCA_SUB(2, s1, s2); DCA_SUB(3, s2, s3); DCA_SUB(4, s3, s4); DCA_SUB(5, s4, s5); DCA_SUB(6, s5, c4);
-    if (stop != ST_RUNNING) break;
+    if (stop != ST_RUNNING) { ++it; break; }
   }
+  // (it = the number of events this unit processed)
 #ifdef DCA_PHASE_CLOCK
   if (lane == 0) {
     for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[3][i], (unsigned long long)ph[i]);
@@ -1540,9 +1556,11 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   if (lane == 0) {
     const Ev& ev = sm.ev[cur];  // the next event to process (popped, its new events not pushed yet)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g->stats[k] = e.stats[k];
-    g->n_end = e.n_end; g->next_id = e.next_id; g->ndraws = e.ndraws;
-    g->iter = e.iter; g->loss_n = e.loss_n; g->loss_sum = e.loss_sum;
+    for (int k = 0; k < 8; ++k) g->stats[k] += (long long)e.stats[k];
+    g->n_end = e.n_end; g->next_id = e.next_id; g->ndraws = e.dbase + e.dpos;
+    g->iter += it;
+    g->loss_n += it - (sm.status == ST_NAN_LOSS ? 1 : 0);
+    g->loss_sum = e.loss_sum;
     g->ev_time = ev.time; g->ev_type = ev.type; g->ev_cell = ev.cell; g->ev_ch = ev.ch; g->ev_hoff = ev.hoff;
     g->status = sm.status;
   }
