@@ -1,33 +1,37 @@
 // dca_fast.cuh -- the throughput kernel of libdca_b200 (FAST arithmetic order).
 //
-// One CTA of 128 threads per replica, resident for the whole launch:
+// A launch is cut into UNITS (replica, chunk of 4096 events), one CTA of 128 threads each, chained per replica:
 //   warps 0-2  "agent" threads (96): the value function and the TDC update.
 //              Lane r (0..6; lane 7 idles) of 8-lane group g (0..11) owns row r of
 //              feature plane f = 12*slot + g for slot = 0..5.  wGradCorr (6 x 7 floats
 //              per lane, never read by another thread) lives in Blackwell tensor memory
-//              used as a per-thread scratchpad (tcgen05.ld / st; or in registers with
-//              DCA_WG_REGS), wNet in shared memory (the afterstate evaluation needs it
-//              with a flexible lane mapping).  96 registers, 43.6 KB -> 5 CTAs per SM.
-//   warp 3     "event" warp: event queue, random numbers, statistics, grid bits,
-//              stop rules (environmentStep, src/Simulator.hs:101-134).  It is the longest
-//              dependency chain of an event, so agent warp 1 builds the next event's
-//              candidate channels for it once its own dense pass is done.
+//              used as a per-thread scratchpad (tcgen05.ld / st), wNet in shared memory
+//              (the afterstate evaluation needs it with a flexible lane mapping).
+//              96 registers, 44.3 KB -> 5 CTAs per SM.
+//   warp 3     "event" warp: event queue, random numbers, statistics, grid bits, candidate
+//              lists, stop rules (environmentStep, src/Simulator.hs:101-134).  It runs ONE
+//              STEP AHEAD of the agents: what an event needs from the queue depends on
+//              whether it has a candidate, not on which channel is chosen.
 //
-// Per event (runStep, src/SimRunner.hs:60-97) -- two CTA barriers:
-//   B1 -> agents: V(s) = x.w from the plane sums (butterfly), then every candidate
-//         channel on its own 8-lane group: the two planes the action touches are
-//         re-evaluated and substituted into the V tree (selectAction,
-//         src/Simulator.hs:185-205 with incAfterStateFreps, src/Gridfuncs.hs:186-252).
-//         event warp: queue pre-scan, random draws (V(s) is published by the agents).
-//   B2 -> every thread: argmax (last maximum wins, src/AccUtils.hs:203-208) and the
-//         TD scalars (src/Agent.hs:62-78), replicated.
-//         agents: dense w / wGradCorr update (src/Agent.hs:67-76) fused with moving
-//         frep / cnt2 to the chosen afterstate (the owners of the touched rows do it)
-//         and with the next event's row sums.
-//         event warp, concurrently: grid bit (src/Gridfuncs.hs:105-110), statistics,
-//         new events, the next event (published to agent warp 1 through named barrier 1,
-//         which then builds its candidate channels), stop rules.
-//   -> B1
+// Per event (runStep, src/SimRunner.hs:60-97) the two sides meet at named barriers that
+// carry exactly the data dependencies (see the barrier helpers below):
+//   agents:  V(s) = x.w from the plane sums (butterfly), then every candidate channel on
+//            its own 8-lane group: the two planes the action touches are re-evaluated and
+//            substituted into the V tree (selectAction, src/Simulator.hs:185-205 with
+//            incAfterStateFreps, src/Gridfuncs.hs:186-252)
+//            -- barrier 2 (agents only): all q written --
+//            argmax (last maximum wins, src/AccUtils.hs:203-208) and the TD scalars
+//            (src/Agent.hs:62-78), replicated per agent thread; warp 0 publishes the decision
+//            -- barrier 3 --
+//            dense w / wGradCorr update (src/Agent.hs:67-76) fused with moving frep / cnt2 to
+//            the chosen afterstate (the owners of the touched rows do it) and with the next
+//            event's row sums
+//            -- barrier 4: wait for the next event's record --
+//   event:   pop of the NEXT event (ahead of the agents) -- barrier 3: the decision --
+//            grid bit (src/Gridfuncs.hs:105-110), END key / reassign, row masks,
+//            -- barrier 1: cnt2 is in its afterstate (agent warp 2) -- candidate list of the
+//            next event, statistics, stop rules -- barrier 4: publish (no wait) --
+//            push of the next event's new events
 //
 // The fp32 arithmetic is the FAST order specified in DESIGN.md ("Arithmetic
 // orders"; the CPU checker restates it independently): every operation is an explicit
