@@ -28,7 +28,7 @@ import DcaB200.FFI
 import Foreign.C.String (peekCString)
 import Foreign.C.Types
 import Foreign.Marshal.Alloc (alloca)
-import Foreign.Marshal.Array (allocaArray, peekArray, withArray, withArrayLen)
+import Foreign.Marshal.Array (allocaArray, peekArray, withArray)
 import Foreign.Ptr (nullPtr)
 import Foreign.Storable (peek, poke)
 import System.IO.Unsafe (unsafePerformIO)

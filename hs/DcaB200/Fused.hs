@@ -2,9 +2,8 @@
 -- (runPeriod, src/SimRunner.hs:132-178, including environmentStep, src/Simulator.hs:101-134:
 -- the event queue, the random numbers and the statistics live on the device).
 -- `runSimGpu` is what `runSim` (src/SimRunner.hs:206-243) becomes for `--backend gpu`
--- when more than one replica is requested or `--fused` is given; reports keep the
--- reference's format because they are produced by the reference's own Stats module
--- from the counters read back.
+-- when more than one replica is requested or `--fused` is given; the period report keeps the
+-- reference's format (`periodReport` below restates `Stats.hs:108-115` on the counters read back).
 --
 -- EXPERIMENTAL / NOT COMPILED IN THIS REPOSITORY (no GHC in the build image); see INTEGRATION.md.  Until it
 -- has been built with GHC 8.4 treat it as a reviewed sketch: the C ABI underneath is what is tested.
@@ -22,7 +21,6 @@ import Foreign.Marshal.Array (allocaArray, peekArray)
 import Foreign.Ptr
 import Foreign.Storable (peek, pokeByteOff)
 import Opt
-import Stats
 import Text.Printf (printf)
 
 -- | per-replica status word = SimStop (src/SimRunner.hs:45-50)
