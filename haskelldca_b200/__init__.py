@@ -6,7 +6,7 @@ the reference's module API (Opt / Simulator / SimRunner / Gridfuncs / Gridneighs
 """
 from . import _ffi  # noqa: F401
 from .opt import Opt, get_opts  # noqa: F401
-from .simulator import Replicas, allreduce_stats  # noqa: F401
+from .simulator import Replicas, allreduce_stats, run_many  # noqa: F401
 from . import agent, gridfuncs, gridneighs, sim_runner, stats  # noqa: F401
 
-__all__ = ["Opt", "get_opts", "Replicas", "allreduce_stats", "agent", "gridfuncs", "gridneighs", "sim_runner", "stats"]
+__all__ = ["Opt", "get_opts", "Replicas", "allreduce_stats", "run_many", "agent", "gridfuncs", "gridneighs", "sim_runner", "stats"]

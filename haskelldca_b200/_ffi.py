@@ -89,6 +89,9 @@ SYMBOLS = {
     "dca_set_rng_tape": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]),
     "dca_set_rng_mt19937": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_size_t]),
     "dca_run": (C.c_int, [C.c_void_p, C.c_int64]),
+    "dca_run_async": (C.c_int, [C.c_void_p, C.c_int64]),
+    "dca_wait": (C.c_int, [C.c_void_p]),
+    "dca_run_many": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64]),
     "dca_run_unit_events": (C.c_int64, []),
     "dca_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "dca_last_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

@@ -178,6 +178,7 @@ struct dca_handle {
   unsigned* d_units = nullptr;  // FAST run kernel: chunks of replica r done in the current launch
   std::string err;
   float last_ms = 0.f;
+  bool pending = false;  // dca_run_async enqueued a launch that dca_wait has not collected yet
   long long launches = 0;
   int warps = 4;
   OpScratch scratch;  // staging of dca_write_state (device + pinned host), allocated at first use
@@ -190,6 +191,15 @@ int fail(dca_handle* h, int code, const char* msg) {
   if (h) h->err = msg;
   return code;
 }
+
+// a launch of dca_run_async still in flight is collected before anything else touches the handle
+#define SETTLE(h)                                   \
+  do {                                              \
+    if ((h) && (h)->pending) {                      \
+      const int rc_settle_ = dca_wait(h);           \
+      if (rc_settle_) return rc_settle_;            \
+    }                                               \
+  } while (0)
 
 int scratch_alloc(dca_handle* h, OpScratch& s, int device, cudaStream_t stream);
 int scratch_reserve(dca_handle* h) { return scratch_alloc(h, h->scratch, h->device, h->stream); }
@@ -323,6 +333,7 @@ const char* dca_last_error(const dca_handle* h) {
 }
 
 int dca_destroy(dca_handle* h) {
+  if (h && h->pending) dca_wait(h);
   if (!h) return DCA_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -428,6 +439,7 @@ int dca_create(const dca_config* cfg, dca_handle** out) {
 }
 
 int dca_reset(dca_handle* h) {
+  SETTLE(h);
   if (!h) return DCA_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaEventRecord(h->ev0, h->stream));
@@ -442,6 +454,7 @@ int dca_reset(dca_handle* h) {
 int dca_set_params(dca_handle* h, const double* call_dur, const double* call_dur_hoff,
                    const double* call_rate, const double* hoff_prob, const float* alpha_net,
                    const float* alpha_avg, const float* alpha_grad) {
+  SETTLE(h);
   if (!h) return DCA_ERR_ARG;
   CK(cudaSetDevice(h->device));
   int rc = DCA_OK;
@@ -462,6 +475,7 @@ int dca_set_params(dca_handle* h, const double* call_dur, const double* call_dur
 
 int dca_set_rng_tape(dca_handle* h, int32_t replica, const uint64_t* words, const double* neglog,
                      size_t n) {
+  SETTLE(h);
   if (bad_replica(h, replica) || !words || !neglog) return fail(h, DCA_ERR_ARG, "dca_set_rng_tape: bad argument");
   if (h->cfg.rng_mode != DCA_RNG_TAPE) return fail(h, DCA_ERR_STATE, "dca_set_rng_tape: handle is not in DCA_RNG_TAPE mode");
   CK(cudaSetDevice(h->device));
@@ -475,6 +489,7 @@ int dca_set_rng_tape(dca_handle* h, int32_t replica, const uint64_t* words, cons
 }
 
 int dca_set_rng_mt19937(dca_handle* h, int32_t replica, uint64_t seed, size_t n_draws) {
+  SETTLE(h);
   if (bad_replica(h, replica)) return fail(h, DCA_ERR_ARG, "dca_set_rng_mt19937: bad replica");
   // pureMT seed (mersenne-random-pure64) == MT19937-64 init_genrand64(seed);
   // randomDouble = (w >> 11) / 2^53; exponential = -log(u) * mean with the host libm.
@@ -489,8 +504,22 @@ int dca_set_rng_mt19937(dca_handle* h, int32_t replica, uint64_t seed, size_t n_
   return dca_set_rng_tape(h, replica, w.data(), nl.data(), n_draws);
 }
 
-int dca_run(dca_handle* h, int64_t max_events) {
+int dca_wait(dca_handle* h) {
+  if (!h) return fail(h, DCA_ERR_ARG, "dca_wait: null handle");
+  if (!h->pending) return DCA_OK;
+  h->pending = false;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  return DCA_OK;
+}
+
+int dca_run_async(dca_handle* h, int64_t max_events) {
   if (!h || max_events < 0) return fail(h, DCA_ERR_ARG, "dca_run: bad argument");
+  if (h->pending) {  // one launch in flight per handle: collect the previous one first
+    const int rcw = dca_wait(h);
+    if (rcw) return rcw;
+  }
   CK(cudaSetDevice(h->device));
   if (h->cfg.rng_mode == DCA_RNG_TAPE)  // a replica without its 49 initial draws was never initialised (DCA_UNINITIALIZED)
     for (int i = 0; i < h->n; ++i)
@@ -540,9 +569,32 @@ int dca_run(dca_handle* h, int64_t max_events) {
   h->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->pending = true;
   return DCA_OK;
+}
+
+int dca_run(dca_handle* h, int64_t max_events) {
+  const int rc = dca_run_async(h, max_events);
+  return rc ? rc : dca_wait(h);
+}
+
+// launch on every handle (typically one per GPU of the box), then collect them all: the devices run side by side
+// although the caller is a single thread
+int dca_run_many(dca_handle** handles, int32_t n, int64_t max_events) {
+  dca_handle* h = nullptr;
+  if (!handles || n <= 0) return fail(h, DCA_ERR_ARG, "dca_run_many: bad argument");
+  for (int i = 0; i < n; ++i)
+    if (!handles[i]) return fail(h, DCA_ERR_ARG, "dca_run_many: null handle");
+  int first = DCA_OK;
+  for (int i = 0; i < n; ++i) {
+    const int rc = dca_run_async(handles[i], max_events);
+    if (rc && !first) first = rc;
+  }
+  for (int i = 0; i < n; ++i) {
+    const int rc = dca_wait(handles[i]);
+    if (rc && !first) first = rc;
+  }
+  return first;
 }
 
 int64_t dca_run_unit_events(void) { return kFastChunkEvents; }
@@ -580,6 +632,7 @@ static int step_launch(dca_handle* h, int replica, int mode, int r, int c, int i
 }
 
 int dca_get_action(dca_handle* h, int32_t replica, int32_t r, int32_t c, int32_t is_end, int32_t* ch) {
+  SETTLE(h);
   if (!ch) return fail(h, DCA_ERR_ARG, "dca_get_action: null output");
   StepOut o{};
   int rc = step_launch(h, replica, 0, r, c, is_end, -1, 0.f, 0.f, 0.f, &o);
@@ -591,6 +644,7 @@ int dca_get_action(dca_handle* h, int32_t replica, int32_t r, int32_t c, int32_t
 int dca_grid_step_train(dca_handle* h, int32_t replica, float alpha_net, float alpha_avg,
                         float alpha_grad, int32_t is_end, int32_t r, int32_t c, int32_t ch,
                         float* loss, int32_t* loss_is_nan, int64_t* reward) {
+  SETTLE(h);
   StepOut o{};
   int rc = step_launch(h, replica, 1, r, c, is_end, ch, alpha_net, alpha_avg, alpha_grad, &o);
   if (rc) return rc;
@@ -602,6 +656,7 @@ int dca_grid_step_train(dca_handle* h, int32_t replica, float alpha_net, float a
 
 int dca_read_state(dca_handle* h, int32_t replica, uint8_t* grid, int64_t* frep, float* wnet,
                    float* wgrad, float* avg_reward, int64_t* iter, dca_event* next_event) {
+  SETTLE(h);
   if (bad_replica(h, replica)) return fail(h, DCA_ERR_ARG, "dca_read_state: bad replica");
   CK(cudaSetDevice(h->device));
   k_unpack<<<1, 256, 0, h->stream>>>(h->d_states + replica, h->d_view);
@@ -642,6 +697,7 @@ int dca_read_state(dca_handle* h, int32_t replica, uint8_t* grid, int64_t* frep,
 
 int dca_write_state(dca_handle* h, int32_t replica, const uint8_t* grid, const float* wnet,
                     const float* wgrad, const float* avg_reward) {
+  SETTLE(h);
   if (bad_replica(h, replica)) return fail(h, DCA_ERR_ARG, "dca_write_state: bad replica");
   CK(cudaSetDevice(h->device));
   RepState* st = h->d_states + replica;
@@ -705,6 +761,7 @@ size_t dca_checkpoint_size(const dca_handle* h) {
 }
 
 int dca_checkpoint_save(dca_handle* h, void* buf, size_t size) {
+  SETTLE(h);
   if (!h || !buf || size < dca_checkpoint_size(h)) return fail(h, DCA_ERR_ARG, "dca_checkpoint_save: bad argument");
   CK(cudaSetDevice(h->device));
   CkptHeader hd{kCkptMagic, kCkptVersion, (uint32_t)sizeof(RepState), h->n, h->cfg.order, h->cfg.rng_mode, 0,
@@ -717,6 +774,7 @@ int dca_checkpoint_save(dca_handle* h, void* buf, size_t size) {
 }
 
 int dca_checkpoint_load(dca_handle* h, const void* buf, size_t size) {
+  SETTLE(h);
   if (!h || !buf || size < dca_checkpoint_size(h)) return fail(h, DCA_ERR_ARG, "dca_checkpoint_load: bad argument");
   CkptHeader hd;
   memcpy(&hd, buf, sizeof hd);
@@ -760,6 +818,7 @@ static int fetch_one(dca_handle* h, int replica, Summary& s) {
 }
 
 int dca_read_stats(dca_handle* h, int32_t replica, int64_t stats[DCA_N_STATS]) {
+  SETTLE(h);
   if (bad_replica(h, replica) || !stats) return fail(h, DCA_ERR_ARG, "dca_read_stats: bad argument");
   Summary s;
   int rc = fetch_one(h, replica, s);
@@ -769,6 +828,7 @@ int dca_read_stats(dca_handle* h, int32_t replica, int64_t stats[DCA_N_STATS]) {
 }
 
 int dca_read_status(dca_handle* h, int32_t replica, int32_t* status, int64_t* iter, uint64_t* n_draws) {
+  SETTLE(h);
   if (bad_replica(h, replica)) return fail(h, DCA_ERR_ARG, "dca_read_status: bad replica");
   Summary s;
   int rc = fetch_one(h, replica, s);
@@ -780,6 +840,7 @@ int dca_read_status(dca_handle* h, int32_t replica, int32_t* status, int64_t* it
 }
 
 int dca_read_period(dca_handle* h, int32_t replica, float* loss_sum, int64_t* n, int32_t reset) {
+  SETTLE(h);
   if (bad_replica(h, replica)) return fail(h, DCA_ERR_ARG, "dca_read_period: bad replica");
   Summary s;
   int rc = fetch_one(h, replica, s);
@@ -796,6 +857,7 @@ int dca_read_period(dca_handle* h, int32_t replica, float* loss_sum, int64_t* n,
 }
 
 int dca_read_trace(dca_handle* h, int32_t replica, dca_trace* out, size_t cap, size_t* n) {
+  SETTLE(h);
   if (bad_replica(h, replica) || !out) return fail(h, DCA_ERR_ARG, "dca_read_trace: bad argument");
   if (!h->d_trace) return fail(h, DCA_ERR_STATE, "dca_read_trace: handle created with trace_capacity == 0");
   Summary s;
@@ -809,6 +871,7 @@ int dca_read_trace(dca_handle* h, int32_t replica, dca_trace* out, size_t cap, s
 }
 
 int dca_read_summary(dca_handle* h, int32_t* status, int64_t* iter, float* avg_reward, int64_t* stats) {
+  SETTLE(h);
   if (!h) return DCA_ERR_ARG;
   std::vector<Summary> s;
   int rc = fetch_summary(h, s);
@@ -824,6 +887,7 @@ int dca_read_summary(dca_handle* h, int32_t* status, int64_t* iter, float* avg_r
 }
 
 int dca_read_agents(dca_handle* h, float* wnet, float* wgrad, float* avg_reward) {
+  SETTLE(h);
   if (!h) return DCA_ERR_ARG;
   CK(cudaSetDevice(h->device));
   const int chunk = 4096;
@@ -845,6 +909,7 @@ int dca_read_agents(dca_handle* h, float* wnet, float* wgrad, float* avg_reward)
 }
 
 int dca_sum_stats(dca_handle* h, int64_t out[10], void** dev_ptr) {
+  SETTLE(h);
   if (!h) return DCA_ERR_ARG;
   CK(cudaSetDevice(h->device));
   CK(cudaMemsetAsync(h->d_sum, 0, sizeof(long long) * 10, h->stream));

@@ -119,6 +119,14 @@ class Replicas:
         _ffi.check(_ffi.load().dca_run(self.h, int(max_events)), self.h)
         return self.elapsed_ms()
 
+    def run_async(self, max_events: int) -> None:
+        """Enqueue the launch and return; `wait` (or any other call on this object) collects it."""
+        _ffi.check(_ffi.load().dca_run_async(self.h, int(max_events)), self.h)
+
+    def wait(self) -> float:
+        _ffi.check(_ffi.load().dca_wait(self.h), self.h)
+        return self.elapsed_ms()
+
     def elapsed_ms(self) -> float:
         ms = C.c_float()
         _ffi.check(_ffi.load().dca_elapsed_ms(self.h, C.byref(ms)), self.h)
@@ -222,6 +230,15 @@ class Replicas:
         dev = C.c_void_p()
         _ffi.check(_ffi.load().dca_sum_stats(self.h, _ffi.ptr(out), C.byref(dev)), self.h)
         return out, dev.value
+
+
+def run_many(replica_sets, max_events: int) -> list:
+    """dca_run_many: one launch per `Replicas` (typically one per device of the box), all in flight together although
+    the caller is a single thread; returns the device ms of each."""
+    n = len(replica_sets)
+    arr = (C.c_void_p * n)(*[s.h for s in replica_sets])
+    _ffi.check(_ffi.load().dca_run_many(arr, n, int(max_events)), replica_sets[0].h)
+    return [s.elapsed_ms() for s in replica_sets]
 
 
 def allreduce_stats(replica_sets) -> np.ndarray:

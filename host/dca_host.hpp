@@ -231,6 +231,14 @@ class Replicas {
     dca_elapsed_ms(h_, &ms);
     return ms;
   }
+  void runAsync(long long maxEvents) { check(dca_run_async(h_, maxEvents), "dca_run_async"); }  // enqueue and return
+  float wait() {  // collect the launch of runAsync; returns device ms
+    check(dca_wait(h_), "dca_wait");
+    float ms = 0;
+    dca_elapsed_ms(h_, &ms);
+    return ms;
+  }
+  dca_handle* handle() const { return h_; }
   int getAction(int replica, int r, int c, bool isEnd) {  // accFn1
     int32_t ch = -1;
     check(dca_get_action(h_, replica, r, c, isEnd, &ch), "dca_get_action");

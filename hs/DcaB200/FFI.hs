@@ -32,6 +32,10 @@ foreign import ccall safe "dca_set_rng_mt19937" c_dca_set_rng_mt19937
 
 -- fused run: replaces runPeriod's loop of runStep (src/SimRunner.hs:132-178) ------
 foreign import ccall safe "dca_run" c_dca_run :: Ptr DcaHandle -> Int64 -> IO CInt
+-- the same in two halves / over several handles: one Haskell thread keeps a handle per GPU busy (include/dca_b200.h)
+foreign import ccall safe "dca_run_async" c_dca_run_async :: Ptr DcaHandle -> Int64 -> IO CInt
+foreign import ccall safe "dca_wait" c_dca_wait :: Ptr DcaHandle -> IO CInt
+foreign import ccall safe "dca_run_many" c_dca_run_many :: Ptr (Ptr DcaHandle) -> Int32 -> Int64 -> IO CInt
 foreign import ccall safe "dca_elapsed_ms" c_dca_elapsed_ms :: Ptr DcaHandle -> Ptr CFloat -> IO CInt
 
 -- accFn1 / accFn2 on explicit arrays (src/SimRunner.hs:61-62, 211-212) ------------

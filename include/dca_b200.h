@@ -173,6 +173,14 @@ int dca_set_rng_mt19937(dca_handle *h, int32_t replica, uint64_t seed, size_t n_
  * (getAction -> environmentStep -> gridStepTrain each) on the device, stopping
  * early with its own SimStop status.  Returns when the device is done. */
 int dca_run(dca_handle *h, int64_t max_events);
+/* The same in two halves, so that ONE host thread (the Haskell main thread runs runSim, src/SimRunner.hs:206-243, in a
+ * single StateT) can keep every GPU of a box busy with a handle per device: dca_run_async enqueues the launch and
+ * returns, dca_wait blocks until it is done (and is a no-op without a launch in flight); every other call on the handle
+ * collects a launch in flight first.  dca_run_many = dca_run_async on each handle, then dca_wait on each; it returns
+ * the first error.  dca_run(h, n) == dca_run_async(h, n) followed by dca_wait(h). */
+int dca_run_async(dca_handle *h, int64_t max_events);
+int dca_wait(dca_handle *h);
+int dca_run_many(dca_handle **handles, int32_t n, int64_t max_events);
 /* DCA_ORDER_FAST: dca_run cuts a launch into units of this many events per replica (one CTA each, chained in
  * order), so that the device stays evenly loaded to the end of the launch; a replica's state is staged from / to
  * HBM once per unit.  Results do not depend on it. */

@@ -512,3 +512,38 @@ def test_units_of_a_launch_chain_correctly():
     with Replicas(Opt(n_replicas=1, n_events=n, order="fast", rng="philox", rng_seed=5)) as sims:
         sims.run(n)
         assert_state_equal(sims.read_state(0), o.read())
+
+
+def test_async_run_and_run_many_equal_the_blocking_run():
+    """dca_run_async / dca_wait / dca_run_many (one host thread, several handles in flight -- a handle per GPU of the
+    box when there are several, two handles on one device otherwise): the same states as blocking dca_run calls, and
+    any other call on a handle collects its launch in flight first."""
+    import haskelldca_b200 as hd
+    from haskelldca_b200 import Opt, Replicas, _ffi
+
+    ndev = _ffi.load().dca_device_count()
+    kw = [dict(n_replicas=3, n_events=5000, order="fast", rng="philox", rng_seed=3, first_replica=0, device=0),
+          dict(n_replicas=2, n_events=5000, order="fast", rng="philox", rng_seed=3, first_replica=3, hoff_prob=0.15,
+               device=1 if ndev > 1 else 0),
+          dict(n_replicas=1, n_events=700, order="ref", rng="philox", rng_seed=4, device=0)]
+    want = []
+    for k in kw:
+        with Replicas(Opt(**k)) as s:
+            s.run(2000)
+            s.run(k["n_events"])
+            want.append([s.read_state(r) for r in range(k["n_replicas"])])
+    sets = [Replicas(Opt(**k)) for k in kw]
+    try:
+        ms = hd.run_many(sets, 2000)
+        assert len(ms) == 3 and all(m > 0 for m in ms)
+        for s, k in zip(sets, kw):
+            s.run_async(k["n_events"])
+        # (no wait: reading a state collects the launch)
+        for s, k, w in zip(sets, kw, want):
+            for r in range(k["n_replicas"]):
+                assert_state_equal(s.read_state(r), w[r])
+            assert s.wait() > 0  # nothing in flight any more: returns the time of the collected launch
+            assert (s.read_summary()["status"] == _ffi.SUCCESS).all()
+    finally:
+        for s in sets:
+            s.close()
