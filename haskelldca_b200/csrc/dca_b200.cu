@@ -361,6 +361,8 @@ int dca_create(const dca_config* cfg, dca_handle** out) {
     return fail(h, DCA_ERR_ARG, "dca_create: bad order");
   if (cfg->rng_mode != DCA_RNG_TAPE && cfg->rng_mode != DCA_RNG_PHILOX)
     return fail(h, DCA_ERR_ARG, "dca_create: bad rng_mode");
+  if (cfg->n_events < 0 || cfg->n_events > DCA_MAX_EVENTS)  // event ids are 32-bit on the device, up to three per event
+    return fail(h, DCA_ERR_ARG, "dca_create: n_events must be in [0, DCA_MAX_EVENTS = 1.4e9] (the device keeps event ids in 32 bits)");
   if (cfg->hoff_lookahead && cfg->order != DCA_ORDER_REF)
     return fail(h, DCA_ERR_ARG, "dca_create: hoff_lookahead is implemented for DCA_ORDER_REF only (the FAST kernel has no look-ahead path yet)");
   int ndev = 0;

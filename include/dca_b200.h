@@ -42,6 +42,10 @@ extern "C" {
 #define DCA_GRID_SIZE 3430 /* 7*7*70 */
 #define DCA_FREP_SIZE 3479 /* 7*7*71 */
 #define DCA_N_STATS 8
+/* The device keeps event ids (egId, src/EventGen/Internal.hs:44-53: only the tie-break between equal event times) in 32
+ * bits and an event takes at most three (NEW accepted with a hand-off: next arrival, END, HOFF), so a replica's
+ * n_events is limited to 2^32 / 3; iteration and draw counters are 64-bit.  dca_create rejects more (DCA_ERR_ARG). */
+#define DCA_MAX_EVENTS 1400000000LL
 
 /* error codes */
 #define DCA_OK 0

@@ -139,3 +139,20 @@ def test_haskell_patch_applies(tmp_path):
     fused = open(os.path.join(ROOT, "hs", "DcaB200", "Fused.hs")).read()
     assert "gpuGetAction" in backend and "gpuGridStepTrain" in backend and "GpuOrder(..)" in backend
     assert "module DcaB200.Fused (runSimGpu, RngSource(..)" in fused
+
+
+def test_dca_create_rejects_a_run_longer_than_the_32_bit_event_ids_allow():
+    """Argument checks come before the device is touched, so this runs without a GPU: n_events > DCA_MAX_EVENTS is
+    DCA_ERR_ARG (-1), not DCA_ERR_NO_DEVICE."""
+    import ctypes as C
+
+    from haskelldca_b200 import _ffi
+
+    L = _ffi.load()
+    cfg = _ffi.Config()
+    assert L.dca_config_defaults(C.byref(cfg)) == 0
+    cfg.n_replicas = 1
+    cfg.n_events = 1_400_000_001
+    h = C.c_void_p()
+    assert L.dca_create(C.byref(cfg), C.byref(h)) == -1 and not h.value
+    assert b"n_events" in L.dca_last_error(None)
