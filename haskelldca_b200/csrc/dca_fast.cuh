@@ -53,6 +53,27 @@ constexpr int NBLK = 22;      // queue blocks of 32 slots
 constexpr int QCAPS = NBLK * 32;  // 704 >= QCAP: whole blocks can be scanned
 static_assert(QCAPS >= QCAP, "queue blocks");
 
+// Instruction-count switches of the agents' loop (late round 2; every one bit-exact, timed with tools/prof_run.py 4096
+// 10000 20000 on one B200: the agents' chain is what bounds the kernel, and a static instruction less per agent
+// iteration is worth ~0.08 % of throughput -- 918 -> 858 instructions, 324.9 -> 340.1 M events/s):
+//   DCA_TADDR_UNIFORM  the tensor-memory address comes out of a warp reduction, i.e. lives in a uniform register: no
+//                      R2UR in front of every LDTM / STTM (12 per iteration)                           324.9 -> 328.3
+//   DCA_CVT_MIX=2      three of the seven byte -> float conversions of a row on the conversion unit (I2F.U8, one
+//                      instruction each) instead of PRMT + FADD(2); more than three saturate that unit
+//                      (=1: 329.6, =2: 332.6, =3: 331.8, =4 (all seven): 326.9)                         328.3 -> 332.6
+//   DCA_PAD_REUSE      the pad column of a row is stored back as it was loaded: no register zeroed per store   -> 338.6
+//   DCA_SA_DELTA + DCA_STTM_X4  "is this slot's plane the chosen channel" from one difference; the wGradCorr row
+//                      stored as two 4-column pieces (shorter register tuples, fewer moves)                    -> 340.1
+#ifndef DCA_V12_AGENT_LOOP
+#define DCA_TADDR_UNIFORM
+#ifndef DCA_CVT_MIX
+#define DCA_CVT_MIX 2
+#endif
+#define DCA_PAD_REUSE
+#define DCA_SA_DELTA
+#define DCA_STTM_X4
+#endif
+
 // Where wGradCorr lives (see struct Agent) and, with it, how many CTAs share an SM.
 #ifndef DCA_NO_END_SLOT_INDEX
 #define DCA_END_SLOT_INDEX
@@ -186,10 +207,27 @@ struct Row7 {  // one row of the feature representation as floats
 };
 __device__ __forceinline__ Row7 cvt_row(uint2 xb) {
   Row7 x;
+#if defined(DCA_CVT_MIX) && DCA_CVT_MIX >= 4
+  x.a = make_float2((float)(xb.x & 0xFFu), (float)((xb.x >> 8) & 0xFFu));
+#else
   x.a = cvt_pair<0>(xb.x);
+#endif
+#if defined(DCA_CVT_MIX) && DCA_CVT_MIX >= 3
+  x.b = make_float2((float)((xb.x >> 16) & 0xFFu), (float)(xb.x >> 24));
+#else
   x.b = cvt_pair<2>(xb.x);
+#endif
+#if defined(DCA_CVT_MIX) && DCA_CVT_MIX >= 2
+  x.c = make_float2((float)(xb.y & 0xFFu), (float)((xb.y >> 8) & 0xFFu));
+#else
   x.c = cvt_pair<0>(xb.y);
+#endif
+#if defined(DCA_CVT_MIX) && DCA_CVT_MIX >= 1
+  // the odd seventh column on the conversion unit (I2F.U8 with a byte selector: one instruction instead of PRMT + FADD)
+  x.d = (float)((xb.y >> 16) & 0xFFu);
+#else
   x.d = cvt_one<2>(xb.y);
+#endif
   return x;
 }
 // rowdot of the FAST order: even / odd column chains, then e + o
@@ -206,6 +244,12 @@ __device__ __forceinline__ float shfl_xor_ordered(const float v, const int m) {
   float r;
   asm volatile("shfl.sync.bfly.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=f"(r) : "f"(v), "r"(m));
   return r;
+}
+__device__ __forceinline__ void st_shared_f2(float* p, const float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" :: "r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_shared_f1(float* p, const float v) {
+  asm volatile("st.shared.f32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(p)), "f"(v) : "memory");
 }
 __device__ __forceinline__ uint2 badd(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ uint2 bsub(uint2 a, uint2 b) { return make_uint2(a.x - b.x, a.y - b.y); }
@@ -246,11 +290,20 @@ __device__ __forceinline__ WgRow wg_wait(WgRegs& v) {  // (the registers are ope
   g.g6 = __uint_as_float(v.r[6]);
   return g;
 }
-__device__ __forceinline__ void wg_put(Agent& ag, const int j, const WgRow& g) {
+__device__ __forceinline__ void wg_put(Agent& ag, const int j, const WgRow& g, const uint32_t pad = 0u) {
+#ifdef DCA_STTM_X4
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               :: "r"(ag.taddr + 8u * (uint32_t)j), "r"(__float_as_uint(g.g01.x)), "r"(__float_as_uint(g.g01.y)),
+                  "r"(__float_as_uint(g.g23.x)), "r"(__float_as_uint(g.g23.y)) : "memory");
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               :: "r"(ag.taddr + 8u * (uint32_t)j + 4u), "r"(__float_as_uint(g.g45.x)), "r"(__float_as_uint(g.g45.y)),
+                  "r"(__float_as_uint(g.g6)), "r"(pad) : "memory");
+  return;
+#endif
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                :: "r"(ag.taddr + 8u * (uint32_t)j), "r"(__float_as_uint(g.g01.x)), "r"(__float_as_uint(g.g01.y)),
                   "r"(__float_as_uint(g.g23.x)), "r"(__float_as_uint(g.g23.y)), "r"(__float_as_uint(g.g45.x)),
-                  "r"(__float_as_uint(g.g45.y)), "r"(__float_as_uint(g.g6)), "r"(0u) : "memory");
+                  "r"(__float_as_uint(g.g45.y)), "r"(__float_as_uint(g.g6)), "r"(pad) : "memory");
 }
 __device__ __forceinline__ void wg_commit() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 constexpr uint32_t TMEM_COLS = 64;
@@ -266,7 +319,13 @@ __device__ __forceinline__ void tmem_open(SmemF& sm, Agent& ag) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef DCA_TADDR_UNIFORM
+  // (the result of a warp reduction lives in a uniform register: the tensor-memory instructions take their address from
+  //  one, and ptxas otherwise re-converts the address before every one of them)
+  ag.taddr = __reduce_max_sync(0xffffffffu, sm.tmem_base + ((threadIdx.x >> 5) * 32u << 16));
+#else
   ag.taddr = sm.tmem_base + ((threadIdx.x >> 5) * 32u << 16);
+#endif
 }
 __device__ __forceinline__ void tmem_close(SmemF& sm) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -283,7 +342,7 @@ struct WgRegs {
 };
 __device__ __forceinline__ WgRegs wg_get(const Agent& ag, const int j) { return WgRegs{ag.g[j]}; }
 __device__ __forceinline__ WgRow wg_wait(WgRegs& v) { return v.g; }
-__device__ __forceinline__ void wg_put(Agent& ag, const int j, const WgRow& g) { ag.g[j] = g; }
+__device__ __forceinline__ void wg_put(Agent& ag, const int j, const WgRow& g, const uint32_t = 0u) { ag.g[j] = g; }
 __device__ __forceinline__ void wg_commit() {}
 __device__ __forceinline__ void tmem_open(SmemF&, Agent&) {}
 __device__ __forceinline__ void tmem_close(SmemF&) {}
@@ -349,7 +408,14 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
   float rg_acc = 0.0f;
   const Row7 dm = cvt_row(n4b_r);            // the row of N4 \ {cell} as 0.0 / 1.0
   const float sgn = is_end ? -1.0f : 1.0f;
+#ifdef DCA_SA_DELTA
+  const int dact = act - l.g8;
+  // does this lane own a row of plane `act`?  (act - g8 in {0, 12, .., 60}; act = -1 gives -1 - g8 < 0)
+  bool own_act = (unsigned)dact < (unsigned)(SLOTP * NSLOT) && ((unsigned)dact * 43u >> 9) * (unsigned)SLOTP == (unsigned)dact;
+  (void)dact;
+#else
   bool own_act = false;                      // does this lane own a row of plane `act`?
+#endif
   (void)dm; (void)sgn;
   // The warp that owns plane 70 (n_elig) also moves cnt2[act] to the afterstate; it does so up front, where
   // the load latency hides behind the first slot: cg = the cells of N2 u {cell} where `act` is eligible on
@@ -384,8 +450,14 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     if (UPDATE) {
       // x' = x + s * [cell in N4 \ {cell}], s = +-1 on plane `act` and 0 elsewhere: small integers, exact in
       // fp32, and branch-free, so that the six slot bodies form one basic block
+#ifdef DCA_SA_DELTA
+      // plane `act` sits in slot j of lane group g8 iff act - g8 == 12 j (group 11 shadows plane 70 in the last slot:
+      // act - 11 == 60 would be channel 71)
+      const float sa = dact == SLOTP * j ? sgn : 0.0f;
+#else
       const float sa = f == act ? sgn : 0.0f;
       own_act = own_act || f == act;
+#endif
       xn.a = __ffma2_rn(f2(sa), dm.a, xo.a);
       xn.b = __ffma2_rn(f2(sa), dm.b, xo.b);
       xn.c = __ffma2_rn(f2(sa), dm.c, xo.c);
@@ -413,12 +485,29 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
         const float g_ = __fmaf_rn(td.ncdot, xn.d, t_);
         w6 = __fsub_rn(w6, g_);
         G.g6 = __fmaf_rn(td.sg, xo.d, G.g6);
+#if defined(DCA_PAD_REUSE) && defined(DCA_WG_TMEM)
+        wg_put(ag, j, G, gin.r[7]);  // (the pad column goes back as it came: no register has to be zeroed for it)
+#else
         wg_put(ag, j, G);
+#endif
       }
       // unconditional: a shadow lane (row 7 -> row 6, group 11 in the last slot -> plane 70) holds the same
       // x, w and wGradCorr as its original and stores the same values to the same address
+#ifdef DCA_W_ST64
+      // (pairs as they come out of the packed FMAs: an STS.128 wants four consecutive registers and costs register moves;
+      //  the same number of shared-memory wavefronts; the pad column keeps its zero)
+      st_shared_f2(&sm.w[0][wo_], w01);
+      st_shared_f2(&sm.w[0][wo_ + 2], w23);
+      st_shared_f2(&sm.w[1][wo_], w45);
+      st_shared_f1(&sm.w[1][wo_ + 2], w6);
+#else
       *reinterpret_cast<float4*>(&sm.w[0][wo_]) = make_float4(w01.x, w01.y, w23.x, w23.y);
+#ifdef DCA_PAD_REUSE
+      *reinterpret_cast<float4*>(&sm.w[1][wo_]) = make_float4(w45.x, w45.y, w6, wb.w);  // (wb.w == 0: the pad column)
+#else
       *reinterpret_cast<float4*>(&sm.w[1][wo_]) = make_float4(w45.x, w45.y, w6, 0.0f);
+#endif
+#endif
     }
     rs[j] = valid ? rowdot2(xn, w01, w23, w45, w6) : 0.0f;
     const float rg = rowdot2(xn, G.g01, G.g23, G.g45, G.g6);
