@@ -62,9 +62,14 @@ static_assert(QCAPS >= QCAP, "queue blocks");
 //                      instruction each) instead of PRMT + FADD(2); more than three saturate that unit
 //                      (=1: 329.6, =2: 332.6, =3: 331.8, =4 (all seven): 326.9)                         328.3 -> 332.6
 //   DCA_PAD_REUSE      the pad column of a row is stored back as it was loaded: no register zeroed per store   -> 338.6
+//   (bmad)             `is_end ? x - m : x + m` on packed bytes as one IMAD per word with the sign in a register   858 -> 826 instr.
 //   DCA_SA_DELTA + DCA_STTM_X4  "is this slot's plane the chosen channel" from one difference; the wGradCorr row
 //                      stored as two 4-column pieces (shorter register tuples, fewer moves)                    -> 340.1
-#ifndef DCA_V12_AGENT_LOOP
+#ifdef DCA_V12_AGENT_LOOP
+#ifndef DCA_CVT_MIX
+#define DCA_CVT_MIX 0
+#endif
+#else
 #define DCA_TADDR_UNIFORM
 #ifndef DCA_CVT_MIX
 #define DCA_CVT_MIX 2
@@ -205,29 +210,26 @@ struct Row7 {  // one row of the feature representation as floats
   float2 a, b, c;
   float d;
 };
+#ifndef DCA_CVT_MIX_EVAL  // the candidate evaluation is not where the conversion unit is busy: all seven there (345.0 -> 346.6)
+#ifdef DCA_V12_AGENT_LOOP
+#define DCA_CVT_MIX_EVAL 0
+#else
+#define DCA_CVT_MIX_EVAL 4
+#endif
+#endif
+// MIX of the seven columns go through the conversion unit (I2F.U8 with a byte selector, one instruction each), the
+// others through PRMT + FADD(2) on the ALU / FMA pipes: 0 = none, 1 = column 6, 2 = columns 4-6, 3 = 2-6, 4 = all
+template <int MIX = DCA_CVT_MIX>
 __device__ __forceinline__ Row7 cvt_row(uint2 xb) {
   Row7 x;
-#if defined(DCA_CVT_MIX) && DCA_CVT_MIX >= 4
-  x.a = make_float2((float)(xb.x & 0xFFu), (float)((xb.x >> 8) & 0xFFu));
-#else
-  x.a = cvt_pair<0>(xb.x);
-#endif
-#if defined(DCA_CVT_MIX) && DCA_CVT_MIX >= 3
-  x.b = make_float2((float)((xb.x >> 16) & 0xFFu), (float)(xb.x >> 24));
-#else
-  x.b = cvt_pair<2>(xb.x);
-#endif
-#if defined(DCA_CVT_MIX) && DCA_CVT_MIX >= 2
-  x.c = make_float2((float)(xb.y & 0xFFu), (float)((xb.y >> 8) & 0xFFu));
-#else
-  x.c = cvt_pair<0>(xb.y);
-#endif
-#if defined(DCA_CVT_MIX) && DCA_CVT_MIX >= 1
-  // the odd seventh column on the conversion unit (I2F.U8 with a byte selector: one instruction instead of PRMT + FADD)
-  x.d = (float)((xb.y >> 16) & 0xFFu);
-#else
-  x.d = cvt_one<2>(xb.y);
-#endif
+  if (MIX >= 4) x.a = make_float2((float)(xb.x & 0xFFu), (float)((xb.x >> 8) & 0xFFu));
+  else x.a = cvt_pair<0>(xb.x);
+  if (MIX >= 3) x.b = make_float2((float)((xb.x >> 16) & 0xFFu), (float)(xb.x >> 24));
+  else x.b = cvt_pair<2>(xb.x);
+  if (MIX >= 2) x.c = make_float2((float)(xb.y & 0xFFu), (float)((xb.y >> 8) & 0xFFu));
+  else x.c = cvt_pair<0>(xb.y);
+  if (MIX >= 1) x.d = (float)((xb.y >> 16) & 0xFFu);
+  else x.d = cvt_one<2>(xb.y);
   return x;
 }
 // rowdot of the FAST order: even / odd column chains, then e + o
@@ -253,6 +255,15 @@ __device__ __forceinline__ void st_shared_f1(float* p, const float v) {
 }
 __device__ __forceinline__ uint2 badd(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ uint2 bsub(uint2 a, uint2 b) { return make_uint2(a.x - b.x, a.y - b.y); }
+// a + s * b on packed bytes, s = +-1 as a register (s = -1: a - b mod 2^32, bytewise exact while no byte borrows): one
+// IMAD per word where `is_end ? bsub : badd` costs a negation or a select more
+__device__ __forceinline__ uint2 bmad(uint2 a, uint2 b, int s) {
+#ifdef DCA_V12_AGENT_LOOP
+  return s < 0 ? bsub(a, b) : badd(a, b);
+#else
+  return make_uint2(a.x + b.x * (uint32_t)s, a.y + b.y * (uint32_t)s);
+#endif
+}
 
 // ---------------------------------------------------------------------------
 // Agent side
@@ -275,6 +286,13 @@ struct WgRegs {    // a row in flight: valid after wg_wait
 };
 __device__ __forceinline__ WgRegs wg_get(const Agent& ag, const int j) {
   WgRegs v;
+#ifdef DCA_LDTM_X4
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]) : "r"(ag.taddr + 8u * (uint32_t)j));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7]) : "r"(ag.taddr + 8u * (uint32_t)j + 4u));
+  return v;
+#endif
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
                : "r"(ag.taddr + 8u * (uint32_t)j));
@@ -426,7 +444,7 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
     const uint2 cr = *reinterpret_cast<const uint2*>(&sm.cnt2[co]);
     const uint32_t want = is_end ? 1u : 0u;
     cg = make_uint2(n2b_r.x & eq_bytes(cr.x, want), n2b_r.y & eq_bytes(cr.y, want));
-    *reinterpret_cast<uint2*>(&sm.cnt2[co]) = is_end ? bsub(cr, n2b_r) : badd(cr, n2b_r);
+    *reinterpret_cast<uint2*>(&sm.cnt2[co]) = bmad(cr, n2b_r, is_end ? -1 : 1);
   }
   if (UPDATE && SIGNAL && wid == 2) cand_signal();  // warp-uniform: cnt2 is in its afterstate
 #pragma unroll
@@ -464,7 +482,7 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
       xn.d = __fmaf_rn(sa, dm.d, xo.d);
       if (last && wid == 2 && act >= 0) {  // warp-uniform: the owners of plane 70 (n_elig)
         if (f == NCH) {  // (the shadow lanes -- row 7, group 11 -- compute and store the same values as their originals)
-          const uint2 eb = is_end ? badd(xb, cg) : bsub(xb, cg);
+          const uint2 eb = bmad(xb, cg, is_end ? 1 : -1);
           xn = cvt_row(eb);
           *reinterpret_cast<uint2*>(&sm.x[xo_]) = eb;
         }
@@ -517,7 +535,7 @@ __device__ __forceinline__ void dense_pass(SmemF& sm, Agent& ag, const Lane& l, 
   if (UPDATE && own_act && l.rv) {  // the afterstate row of plane `act` (every slot has read its x by now)
     uint2* xp = reinterpret_cast<uint2*>(&sm.x[act * PLANE + l.r * ROWPAD]);
     const uint2 xb_act = *xp;
-    *xp = is_end ? bsub(xb_act, n4b_r) : badd(xb_act, n4b_r);
+    *xp = bmad(xb_act, n4b_r, is_end ? -1 : 1);
   }
   // plane sums: the xor-butterfly 1,2,4 over the 8 lanes (rows) of a group, for six slots at once as a
   // reduce-scatter -- at every step a lane keeps half of its values and hands the other half to its
@@ -615,13 +633,13 @@ __device__ __forceinline__ void q_rows(const CandLoads& c, const QConst& qc, con
                                        const uint2 n4b_r, const uint2 n2b_r, float& rowP, float& rowE) {
   const uint32_t want = is_end ? 1u : 0u;
   // channel plane: x' = x +- [cell in N4 \ {cell}]   (Gridfuncs.hs:212-217)
-  const uint2 xr = is_end ? bsub(c.xr, n4b_r) : badd(c.xr, n4b_r);
-  const float rp = rowdot2(cvt_row(xr), make_float2(c.wa.x, c.wa.y), make_float2(c.wa.z, c.wa.w),
+  const uint2 xr = bmad(c.xr, n4b_r, is_end ? -1 : 1);
+  const float rp = rowdot2(cvt_row<DCA_CVT_MIX_EVAL>(xr), make_float2(c.wa.x, c.wa.y), make_float2(c.wa.z, c.wa.w),
                            make_float2(c.wb.x, c.wb.y), c.wb.z);
   // n_elig plane: e' = e -+ [cell in N2 u {cell} and ch eligible there on grid']  (Gridfuncs.hs:220-252)
   const uint2 cg = make_uint2(n2b_r.x & eq_bytes(c.cr.x, want), n2b_r.y & eq_bytes(c.cr.y, want));
-  const uint2 er = is_end ? badd(qc.x70, cg) : bsub(qc.x70, cg);
-  const float re = rowdot2(cvt_row(er), make_float2(qc.e_a.x, qc.e_a.y), make_float2(qc.e_a.z, qc.e_a.w),
+  const uint2 er = bmad(qc.x70, cg, is_end ? 1 : -1);
+  const float re = rowdot2(cvt_row<DCA_CVT_MIX_EVAL>(er), make_float2(qc.e_a.x, qc.e_a.y), make_float2(qc.e_a.z, qc.e_a.w),
                            make_float2(qc.e_b.x, qc.e_b.y), qc.e_b.z);
   rowP = rv ? rp : 0.0f;
   rowE = rv ? re : 0.0f;
