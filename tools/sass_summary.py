@@ -17,7 +17,7 @@ for line in sass.split("\n"):
     m = re.search(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
     if m and cur:
         funcs[cur].append(m.group(1))
-KEY = ["LDTM", "STTM", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "PRMT", "IMAD", "LDS", "STS", "SHFL", "REDUX", "CREDUX",
+KEY = ["LDTM", "STTM", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "PRMT", "I2F", "IMAD", "R2UR", "MOV", "LDS", "STS", "SHFL", "REDUX", "CREDUX",
        "VOTE", "BAR", "LDL", "STL", "LDG", "STG", "DADD", "DMUL", "DFMA", "CALL", "BRA"]
 print(f"library: {os.path.relpath(lib, ROOT)}\n")
 for name, ops in funcs.items():
