@@ -363,8 +363,6 @@ int dca_create(const dca_config* cfg, dca_handle** out) {
     return fail(h, DCA_ERR_ARG, "dca_create: bad rng_mode");
   if (cfg->n_events < 0 || cfg->n_events > DCA_MAX_EVENTS)  // event ids are 32-bit on the device, up to three per event
     return fail(h, DCA_ERR_ARG, "dca_create: n_events must be in [0, DCA_MAX_EVENTS = 1.4e9] (the device keeps event ids in 32 bits)");
-  if (cfg->hoff_lookahead && cfg->order != DCA_ORDER_REF)
-    return fail(h, DCA_ERR_ARG, "dca_create: hoff_lookahead is implemented for DCA_ORDER_REF only (the FAST kernel has no look-ahead path yet)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(h, DCA_ERR_NO_DEVICE, "dca_create: no CUDA device (there is no CPU fallback)");
@@ -429,6 +427,7 @@ int dca_create(const dca_config* cfg, dca_handle** out) {
   h->warps = 4;  // both kernels use 128-thread CTAs (warps_per_replica is accepted and ignored)
   if ((rc = set_smem(h, fast::k_run_fast<false>, sizeof(fast::SmemF))) ||
       (rc = set_smem(h, fast::k_run_fast<true>, sizeof(fast::SmemF))) ||
+      (rc = set_smem(h, fast::k_run_fast<true, true>, sizeof(fast::SmemLA))) ||
       (rc = set_smem(h, fast::k_step_fast, sizeof(fast::SmemF))) ||
       (rc = set_smem(h, k_run<ORDER_REF, false>)) || (rc = set_smem(h, k_run<ORDER_REF, true>)) ||
       (rc = set_smem(h, k_step<ORDER_REF>)) || (rc = set_smem(h, k_gf_violates)))
@@ -562,7 +561,9 @@ int dca_run_async(dca_handle* h, int64_t max_events) {
     a.chunk_done = h->d_units;
     CK(cudaMemsetAsync(h->d_units, 0, sizeof(unsigned) * (size_t)h->n, h->stream));
     const dim3 fgrid((unsigned)(chunks * (long long)h->n));
-    if (trace_fast) fast::k_run_fast<true><<<fgrid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
+    // (hand-off look-ahead: its own instantiation, so that the two hot ones carry none of its code; it has the extra barrier too)
+    if (a.lookahead) fast::k_run_fast<true, true><<<fgrid, fast::NT, sizeof(fast::SmemLA), h->stream>>>(a);
+    else if (trace_fast) fast::k_run_fast<true><<<fgrid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
     else fast::k_run_fast<false><<<fgrid, fast::NT, sizeof(fast::SmemF), h->stream>>>(a);
   } else {
     if (trace) k_run<ORDER_REF, true><<<grid, block, smem, h->stream>>>(a);

@@ -105,6 +105,11 @@ struct Ev {  // an event and its candidate set (double-buffered: the event warp 
   uint8_t cand[72];      // candidate channels, ascending
 };
 
+struct LaRec {      // the channels eligible at the hand-off target cell on the current grid (event warp -> agents)
+  uint32_t hm[3];   // as a mask ...
+  int nh;           // ... their number ...
+  uint8_t hcand[72];  // ... and ascending
+};
 struct alignas(16) SmemF {
   float w[2][WH];           // wNet: columns 0-3 of row rho = f*7+r at [0][rho*4+c], columns 4-6 at [1][rho*4+c-4]
   uint8_t x[WPAD];          // frep, [f][r][8]
@@ -135,8 +140,17 @@ struct alignas(16) SmemF {
   uint2 n2rows[NCELL];      // ... and of N2(cell) u {cell}  (copied from the constant tables: a shared-memory load
                             // with a computed index is ~5 x faster than a constant-memory one)
 };
-static_assert(sizeof(SmemF) <= (233472 / DCA_MIN_CTAS - 1024), "shared memory per CTA: DCA_MIN_CTAS of them must fit an SM");
-static_assert(sizeof(SmemF) % 16 == 0, "SmemF size");
+// what the hand-off look-ahead instantiation keeps on top (its own type: the hot instantiations are compiled against SmemF
+// alone and stay byte for byte what they were)
+struct alignas(16) SmemLA : SmemF {
+  float qla[72];            // look-ahead values of the candidates of a hand-off END (the selection; sm.q keeps V(afterstate_k))
+  LaRec la[3];              // per event record: the channels eligible at the hand-off target
+  uint32_t pad_la_[2];
+};
+__device__ __forceinline__ SmemLA& la_of(SmemF& sm) { return static_cast<SmemLA&>(sm); }
+__device__ __forceinline__ const SmemLA& la_of(const SmemF& sm) { return static_cast<const SmemLA&>(sm); }
+static_assert(sizeof(SmemLA) <= (233472 / DCA_MIN_CTAS - 1024), "shared memory per CTA: DCA_MIN_CTAS of them must fit an SM");
+static_assert(sizeof(SmemF) % 16 == 0 && sizeof(SmemLA) % 16 == 0, "SmemF size");
 static_assert(offsetof(SmemF, x) % 8 == 0 && offsetof(SmemF, cnt2) % 8 == 0 && offsetof(SmemF, grid) % 16 == 0 &&
               offsetof(SmemF, q_time) % 16 == 0 && offsetof(SmemF, q_id) % 16 == 0 && offsetof(SmemF, q_key) % 16 == 0 &&
               offsetof(SmemF, q_hoff) % 8 == 0 && offsetof(SmemF, ev) % 8 == 0 &&
@@ -715,6 +729,114 @@ __device__ __forceinline__ VTree q_phase(SmemF& sm, const Lane& l, const Ev& ev,
   return t;
 }
 
+// ---------------------------------------------------------------------------
+// Hand-off look-ahead in the FAST order (extension: the reference's TODO, README.md:71-72; specified at
+// dca_config.hoff_lookahead in include/dca_b200.h, oracle: orc_get_action_lookahead).  On the END half of a hand-off
+// (END ch (Just toCell)) the value that SELECTS the channel to free is
+//   qla[k] = max over h eligible at toCell on afterstate_k of V(afterstate_k with h assigned at toCell),
+// V(afterstate_k) when nothing is eligible there; a left fold with `>` over ascending h, as the oracle does it.  Every
+// V is again exactly the dense dot of the materialised state in the FAST tree: up to three planes change -- the freed
+// channel's (-1 on N4(cell) \ {cell}, and +1 on N4(toCell) \ {toCell} when h is that same channel), h's (+1 on
+// N4(toCell) \ {toCell}) and n_elig (+1 where k becomes eligible, then -1 where h was eligible on that afterstate) -- their
+// rows are re-evaluated and their plane sums substituted into the V tree, whose two changed leaves meet at the level of
+// their highest differing index bit.  sm.q keeps the plain values V(afterstate_k): the TD target (Agent.hs:63) is the real
+// afterstate's.  Candidate k sits on lane group k % 12 as in q_phase; all trip counts are warp-uniform.
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void q_lookahead(SmemF& sm, const Lane& l, const Ev& ev, const LaRec& rec, const int n,
+                                         const uint2 n4b_r, const uint2 n2b_r, const VTree& vt) {
+  const int rc = l.rv ? l.r : 6;
+  const int wfirst = l.vw * 4;
+  const int to = ev.hoff;
+  const int nh = rec.nh;
+  const uint32_t hm0 = rec.hm[0], hm1 = rec.hm[1], hm2 = rec.hm[2];
+  uint2 t4, t2;  // row rc of N4(toCell) \ {toCell} and of N2(toCell) u {toCell} as byte masks
+  {
+    const uint2 a = sm.n4rows[to], b = sm.n2rows[to];
+    const int sh = 8 * (rc & 3);
+    t4 = spread7(((rc < 4 ? a.x : a.y) >> sh) & 0x7Fu);
+    t2 = spread7(((rc < 4 ? b.x : b.y) >> sh) & 0x7Fu);
+  }
+  const int pos_to = to + (to * 37 >> 8);
+  const QConst qc = q_const(sm, rc);
+  __syncwarp();  // (sm.q[k] of this group's candidates was written by its row-0 lane in q_phase)
+#pragma unroll 1
+  for (int base = 0; base + wfirst < n; base += SLOTP) {  // warp-uniform trip count
+    const int k = base + l.g8;
+    const int ch = ev.cand[k];  // (k >= n: a stale but valid channel number; masked at the store)
+    const CandLoads ck = q_loads(sm, ch, rc);
+    const int la = ch & 31, hia = ch >> 5;
+    float sibA[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) sibA[i] = __shfl_sync(0xffffffffu, vt.sib[i], la);
+    // freeing ch makes ch itself eligible at the target iff the departing call was its only user within distance 2 of it
+    const bool extra_ok = sm.cnt2[ch * PLANE + pos_to] == 1;
+    const uint32_t lt = (1u << la) - 1u;
+    const int pos = hia == 0 ? __popc(hm0 & lt) : (hia == 1 ? __popc(hm0) + __popc(hm1 & lt) : __popc(hm0) + __popc(hm1) + __popc(hm2 & lt));
+    // the END of ch at the event cell (Gridfuncs.hs:212-252 with diff = -1)
+    const uint2 xk1 = bsub(ck.xr, n4b_r);
+    const uint2 e1 = badd(qc.x70, make_uint2(n2b_r.x & eq_bytes(ck.cr.x, 1u), n2b_r.y & eq_bytes(ck.cr.y, 1u)));
+    const uint2 crk1 = bsub(ck.cr, n2b_r);  // cnt2[ch] on that afterstate
+    float best = 0.0f;
+    bool have = false;
+#pragma unroll 1
+    for (int u = 0; u <= nh; ++u) {  // the merged ascending list: eligible channels, ch at its place (slot `pos`)
+      const bool same = u == pos;
+      const int h = same ? ch : rec.hcand[u < pos ? u : u - 1];
+      const bool active = same ? extra_ok : true;
+      const CandLoads chh = q_loads(sm, h, rc);
+      const int lb = h & 31, hib = h >> 5;
+      // the HOFF arrival taking h at the target on that afterstate (diff = +1)
+      const uint2 xk = same ? badd(xk1, t4) : xk1;
+      const uint2 xh = badd(chh.xr, t4);
+      const uint2 crh = same ? crk1 : chh.cr;
+      const uint2 e2 = bsub(e1, make_uint2(t2.x & eq_bytes(crh.x, 0u), t2.y & eq_bytes(crh.y, 0u)));
+      float Pk = rowdot2(cvt_row<DCA_CVT_MIX_EVAL>(xk), make_float2(ck.wa.x, ck.wa.y), make_float2(ck.wa.z, ck.wa.w),
+                         make_float2(ck.wb.x, ck.wb.y), ck.wb.z);
+      float Ph = rowdot2(cvt_row<DCA_CVT_MIX_EVAL>(xh), make_float2(chh.wa.x, chh.wa.y), make_float2(chh.wa.z, chh.wa.w),
+                         make_float2(chh.wb.x, chh.wb.y), chh.wb.z);
+      float Ep = rowdot2(cvt_row<DCA_CVT_MIX_EVAL>(e2), make_float2(qc.e_a.x, qc.e_a.y), make_float2(qc.e_a.z, qc.e_a.w),
+                         make_float2(qc.e_b.x, qc.e_b.y), qc.e_b.z);
+      if (!l.rv) { Pk = 0.0f; Ph = 0.0f; Ep = 0.0f; }
+#pragma unroll
+      for (int sft = 1; sft < 8; sft <<= 1) {
+        Pk = __fadd_rn(Pk, __shfl_xor_sync(0xffffffffu, Pk, sft));
+        Ph = __fadd_rn(Ph, __shfl_xor_sync(0xffffffffu, Ph, sft));
+        Ep = __fadd_rn(Ep, __shfl_xor_sync(0xffffffffu, Ep, sft));
+      }
+      // the two leaves of the V tree (leaf l = (P[l] + P[l + 32]) + P[l + 64]); h in ch's leaf but another plane: one leaf
+      const bool one_leaf = same || lb == la;
+      float a0 = hia == 0 ? Pk : ck.l0, a1 = hia == 1 ? Pk : ck.l1, a2 = hia == 2 ? Pk : ck.l2;
+      if (!same && lb == la) {
+        if (hib == 0) a0 = Ph;
+        else if (hib == 1) a1 = Ph;
+        else a2 = Ph;
+      }
+      const float b0 = hib == 0 ? Ph : chh.l0, b1 = hib == 1 ? Ph : chh.l1, b2 = hib == 2 ? Ph : chh.l2;
+      float A = __fadd_rn(__fadd_rn(a0, a1), a2), B = __fadd_rn(__fadd_rn(b0, b1), b2);
+      const int merge = one_leaf ? -1 : 31 - __clz(la ^ lb);  // the butterfly level at which leaf lb's block joins leaf la's path
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const float sb = __shfl_sync(0xffffffffu, vt.sib[i], lb);
+        A = __fadd_rn(A, i == merge ? B : sibA[i]);
+        B = __fadd_rn(B, sb);
+      }
+      const float v = __fadd_rn(A, Ep);
+      if (active) {
+        if (!have || v > best) best = v;
+        have = true;
+      }
+    }
+    if (!have) best = sm.q[k];  // nothing is eligible at the target: the hand-off will be rejected
+    if (l.r == 0 && k < n) la_of(sm).qla[k] = best;
+  }
+}
+// index of channel `ch` in the ascending candidate list (warp-wide)
+__device__ __forceinline__ int cand_index(const uint8_t* cand, const int n, const int ch) {
+  int c = 0;
+  for (int k = lane_id(); k < n; k += 32) c += cand[k] < ch ? 1 : 0;
+  return __reduce_add_sync(0xffffffffu, c);
+}
+
 // argpmax (AccUtils.hs:203-208): the largest value, the LAST index among equals;
 // NaNs follow the sequential right fold exactly.  Every warp computes it for itself.
 // cand_lane = cand[lane] (read before the barrier): the chosen channel rides along in the index
@@ -722,6 +844,9 @@ __device__ __forceinline__ VTree q_phase(SmemF& sm, const Lane& l, const Ev& ev,
 // shuffled after the two reductions.  The common case (n <= 32, no NaN) is branch-free; a NaN is
 // mapped to the largest key, so one warp-uniform test after the first reduction finds every
 // uncommon case.  Returns the channel; qbest = q[k].  (n == 0: the result is meaningless.)
+// (TAG: the look-ahead instantiation calls its own copy -- ptxas allocates an out-of-line function's registers across all of its
+//  call sites, and one more caller changes the hot kernels' code)
+template <int TAG = 0>
 __device__ __noinline__ int argmax_uncommon(const float* q, const uint8_t* cand, int n, float& qbest) {
   const int lane = lane_id();
   bool nan = false;
@@ -750,6 +875,7 @@ __device__ __noinline__ int argmax_uncommon(const float* q, const uint8_t* cand,
   qbest = q[best];
   return cand[best];
 }
+template <int TAG = 0>
 __device__ __forceinline__ int argmax_last_warp(const float* q, const uint8_t* cand, const int cand_lane, const int n,
                                                 float& qbest) {
   const int lane = lane_id();
@@ -761,7 +887,7 @@ __device__ __forceinline__ int argmax_last_warp(const float* q, const uint8_t* c
   if (lane >= n) u = 0u;
   const uint32_t m = __reduce_max_sync(0xffffffffu, u);
   const int key = __reduce_max_sync(0xffffffffu, (u == m) ? ((lane << 8) | cand_lane) : -1);
-  if (n > 32 || m == 0xFFFFFFFFu) return argmax_uncommon(q, cand, n, qbest);  // warp-uniform
+  if (n > 32 || m == 0xFFFFFFFFu) return argmax_uncommon<TAG>(q, cand, n, qbest);  // warp-uniform
   // the inverse map gives q[k] bit for bit, except that a best value of -0 comes back as +0: it is only
   // ever added to reward - avgR, which is never -0, so the sum is the same
   qbest = __uint_as_float(m ^ ~((uint32_t)((int32_t)m >> 31) & 0x7FFFFFFFu));
@@ -800,11 +926,9 @@ __device__ __forceinline__ DecidePrep decide_prepare(const SmemF& sm, const Ev& 
   p.alpha_grad = sm.alpha_grad;
   return p;
 }
-__device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const VTree& vt, const DecidePrep& p,
-                                           const int n, float& avgR, int& ncalls) {
+__device__ __forceinline__ Decision decide_from(const Ev& ev, const VTree& vt, const DecidePrep& p, const int n,
+                                                const int act, const float qbest, float& avgR, int& ncalls) {
   Decision d;
-  float qbest;
-  const int act = argmax_last_warp(sm.q, ev.cand, p.cand_lane, n, qbest);  // selectAction, Simulator.hs:202
   d.act = n > 0 ? act : -1;
   const float next_val = n > 0 ? qbest : vt.val;  // no action: nextFrep = frep (Simulator.hs:170-171)
   ncalls = p.ncalls1;
@@ -816,6 +940,21 @@ __device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const 
   d.td.sg = __fmul_rn(p.alpha_grad, __fsub_rn(d.tderr, vt.dotg));
   avgR = __fadd_rn(avgR, __fmul_rn(p.alpha_avg, d.tderr));
   return d;
+}
+__device__ __forceinline__ Decision decide(const SmemF& sm, const Ev& ev, const VTree& vt, const DecidePrep& p,
+                                           const int n, float& avgR, int& ncalls) {
+  float qbest;
+  const int act = argmax_last_warp(sm.q, ev.cand, p.cand_lane, n, qbest);  // selectAction, Simulator.hs:202
+  return decide_from(ev, vt, p, n, act, qbest, avgR, ncalls);
+}
+// the END half of a hand-off under hoff_lookahead: the look-ahead values select, the plain value of the chosen afterstate
+// is the TD target
+__device__ __forceinline__ Decision decide_la(const SmemF& sm, const Ev& ev, const VTree& vt, const DecidePrep& p,
+                                              const int n, float& avgR, int& ncalls) {
+  float qbest;
+  const int act = argmax_last_warp<1>(la_of(sm).qla, ev.cand, p.cand_lane, n, qbest);
+  if (n > 0) qbest = sm.q[cand_index(ev.cand, n, act)];
+  return decide_from(ev, vt, p, n, act, qbest, avgR, ncalls);
 }
 
 // ---------------------------------------------------------------------------
@@ -980,6 +1119,25 @@ __device__ __forceinline__ int agent_candidates(const SmemF& sm, Ev& ev, const i
   }
   if (lane == 0) ev.ncand = base;
   return base;
+}
+
+// hand-off look-ahead: the channels eligible at the hand-off target `to` (cnt2 == 0 there) on the current grid
+__device__ __forceinline__ void la_candidates(const SmemF& sm, LaRec& r, const int to) {
+  const int lane = lane_id();
+  const int pos = to + (to * 37 >> 8);
+  const uint8_t c0 = sm.cnt2[lane * PLANE + pos], c1 = sm.cnt2[(lane + 32) * PLANE + pos];
+  const uint8_t c2 = sm.cnt2[(lane < 6 ? lane + 64 : 0) * PLANE + pos];
+  uint32_t m[3];
+  m[0] = __ballot_sync(0xffffffffu, c0 == 0);
+  m[1] = __ballot_sync(0xffffffffu, c1 == 0);
+  m[2] = __ballot_sync(0xffffffffu, lane < 6 && c2 == 0);
+  int base = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if ((m[j] >> lane) & 1u) r.hcand[base + __popc(m[j] & ((1u << lane) - 1u))] = (uint8_t)(32 * j + lane);
+    base += __popc(m[j]);
+  }
+  if (lane == 0) { r.nh = base; r.hm[0] = m[0]; r.hm[1] = m[1]; r.hm[2] = m[2]; }
 }
 
 // ---- the event queue (EventGen, src/EventGen/Internal.hs:44-53) as a dense slot table with
@@ -1470,7 +1628,7 @@ __device__ __forceinline__ void ev_load(EvRegs& e, const RunArgs& a, const RepSt
 // sync_end (TRACE instantiation: parity traces, verify flags): one more barrier per event so that the
 // event warp sees the afterstate before it hashes / verifies it.
 // ---------------------------------------------------------------------------
-template <bool TRACE>
+template <bool TRACE, bool LA>
 __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState* g, Agent& ag, const int n_ev) {
   constexpr bool sync_end = TRACE;  // (the host launches the TRACE instantiation whenever a verify flag is set)
   const Lane l = make_lane();
@@ -1490,6 +1648,8 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
   for (int it = 0; it < n_ev; ++it) {
     DCA_CLK(c0);
     const Ev& ev = sm.ev[cur];
+    const int la_idx = LA ? cur : 0;
+    (void)la_idx;
     cur = cur == 2 ? 0 : cur + 1;
     const int n = ev.ncand;
     const bool is_end = ev.type == EV_END;
@@ -1497,11 +1657,16 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
     // accFn1 = getAction (Simulator.hs:154-172)
     DecidePrep dp = decide_prepare(sm, ev, n, is_end, avgR, ncalls);
     const VTree vt = q_phase(sm, l, ev, n, is_end, n4b_r, n2b_r);
+    bool la = false;
+    if constexpr (LA) {
+      la = is_end && n > 0 && ev.hoff != HOFF_NONE;  // (uniform) the departure half of a hand-off
+      if (la) q_lookahead(sm, l, ev, la_of(sm).la[la_idx], n, n4b_r, n2b_r, vt);
+    }
     dp.ncdot = -__fmul_rn(dp.c, vt.dotg);
     DCA_CLK(c1);
     agents_q_ready();  // B2
     DCA_CLKB(c2);
-    const Decision d = decide(sm, ev, vt, dp, n, avgR, ncalls);
+    const Decision d = (LA && la) ? decide_la(sm, ev, vt, dp, n, avgR, ncalls) : decide(sm, ev, vt, dp, n, avgR, ncalls);
     if (l.vw == 0) {  // warp-uniform: the event warp takes the decision from here
       if (lane_id() == 0) *reinterpret_cast<int4*>(&sm.pub) = make_int4(d.act, __float_as_int(d.tderr), __float_as_int(avgR), ncalls);
       decision_published();
@@ -1529,7 +1694,7 @@ __device__ __forceinline__ void agent_main(SmemF& sm, const RunArgs& a, RepState
   }
 }
 
-template <bool TRACE>
+template <bool TRACE, bool LA>
 __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState* g, int rep, const int n_ev) {
   constexpr bool sync_end = TRACE;  // (the host launches the TRACE instantiation whenever a verify flag is set)
   const int lane = lane_id();
@@ -1544,6 +1709,11 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
   QBlk qb;
   q_build(sm, qb, e.n_end);
   ev_candidates(sm, sm.ev[0], -1);
+  if (LA) {
+    for (int i = lane; i < 72; i += 32) la_of(sm).la[0].hcand[i] = la_of(sm).la[1].hcand[i] = la_of(sm).la[2].hcand[i] = 0;  // (read speculatively)
+    __syncwarp();
+    if (sm.ev[0].type == EV_END && sm.ev[0].hoff != HOFF_NONE) la_candidates(sm, la_of(sm).la[0], sm.ev[0].hoff);
+  }
   // The event warp runs one step AHEAD of the agents: the new events of an event (ev_env_push needs only whether it
   // has a candidate) are pushed at the end of the previous event's update phase, its successor is popped while the
   // agents evaluate its candidates.  pend_slot / q_overflow carry the result of the push to the event it belongs to.
@@ -1604,6 +1774,7 @@ __device__ __forceinline__ void event_main(SmemF& sm, const RunArgs& a, RepState
     cand_wait();
     DCA_CLKB(s3);
     const int n_next = agent_candidates(sm, nx, en.type, en.cell);
+    if (LA && en.type == EV_END && en.hoff != HOFF_NONE) la_candidates(sm, la_of(sm).la[cur], en.hoff);  // (uniform)
     DCA_CLK(s4);
     // ssIter += 1 (Simulator.hs:131): the replica's iteration count is iter0 + it + 1 from here on
     // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
@@ -1692,7 +1863,7 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 __device__ __forceinline__ void st_release_gpu(unsigned* p, const unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-template <bool TRACE>
+template <bool TRACE, bool LA = false>
 __global__ void __launch_bounds__(NT, DCA_MIN_CTAS) k_run_fast(RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemF& sm = *reinterpret_cast<SmemF*>(smem_raw);
@@ -1713,8 +1884,8 @@ __global__ void __launch_bounds__(NT, DCA_MIN_CTAS) k_run_fast(RunArgs a) {
 #endif
     Agent ag;
     tmem_open(sm, ag);
-    if ((virtual_tid() >> 5) == EVW) event_main<TRACE>(sm, a, g, (int)rep, n_ev);
-    else agent_main<TRACE>(sm, a, g, ag, n_ev);
+    if ((virtual_tid() >> 5) == EVW) event_main<TRACE, LA>(sm, a, g, (int)rep, n_ev);
+    else agent_main<TRACE, LA>(sm, a, g, ag, n_ev);
     tmem_close(sm);
 #ifdef DCA_PHASE_CLOCK
     if (threadIdx.x == 0 && blockIdx.x < 8192) {

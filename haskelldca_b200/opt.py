@@ -34,7 +34,7 @@ class Opt:  # src/Opt.hs:10-25
     first_replica: int = 0
     trace: int = 0                   # per-replica trace capacity
     warps_per_replica: int = 0
-    hoff_lookahead: bool = False     # extension (the reference's TODO, README.md:71-72); order "ref" only
+    hoff_lookahead: bool = False     # extension (the reference's TODO, README.md:71-72); dca_run in either order
 
 
 def get_opts(argv=None, rand: int | None = None) -> Opt:
@@ -62,7 +62,7 @@ def get_opts(argv=None, rand: int | None = None) -> Opt:
     p.add_argument("--device", type=int, default=d.device)
     p.add_argument("--hoff_lookahead", action="store_true",
                    help="Extension (the reference's TODO): on the END half of a hand-off, choose the channel to free by looking ahead "
-                        "at the hand-off arrival in the target cell. --order ref only.")
+                        "at the hand-off arrival in the target cell (dca_run, either --order).")
     a = p.parse_args(argv)
     seed = 0 if a.fixed_rng else (rand if rand is not None else random.getrandbits(64))  # seedParser, Opt.hs:79-82
     kw = {k: v for k, v in vars(a).items() if k != "fixed_rng"}

@@ -114,7 +114,8 @@ typedef struct {
    * On the END half of a hand-off (END ch (Just toCell), src/EventGen.hs:94-109) the channel to free is chosen by
    *   q[k] = max over h eligible at toCell on afterstate_k of V(afterstate_k with h assigned at toCell)
    * (V(afterstate_k) when none is eligible) instead of V(afterstate_k); the TD update still uses the real afterstate.
-   * Implemented by dca_run for DCA_ORDER_REF (dca_create rejects it with DCA_ORDER_FAST). */
+   * Implemented by dca_run in both orders (the fused FAST kernel has its own instantiation for it); the step-wise
+   * operators, whose signatures carry no hand-off target, ignore it. */
   int32_t hoff_lookahead;
   int32_t reserved_;
 } dca_config;

@@ -458,21 +458,23 @@ def test_guard_rails_of_the_c_abi():
             assert sims.sum_stats()[0][9] == 1
 
 
+@pytest.mark.parametrize("order", ["ref", "fast"])
 @pytest.mark.parametrize("rng,kw", [("philox", dict(hoff_prob=0.3)), ("mt19937", dict(hoff_prob=0.15, call_dur_hoff=1.0)),
                                     ("philox", dict(hoff_prob=0.6, call_rate=400.0, call_dur=1.0))])
-def test_handoff_lookahead_matches_the_oracle(rng, kw):
+def test_handoff_lookahead_matches_the_oracle(rng, kw, order):
     """The extension (the reference's TODO, README.md:71-72; include/dca_b200.h dca_config.hoff_lookahead) in the
-    REF-order run kernel against the oracle's first-principles definition: every event bit for bit."""
+    REF-order run kernel and in the fused FAST kernel (its own instantiation, k_run_fast<true, true>) against the
+    oracle's first-principles definition: every event bit for bit."""
     from haskelldca_b200 import Opt, Replicas
-    from haskelldca_b200._ffi import DcaError
 
     n_rep, n_ev = (3, 4000) if rng == "philox" else (1, 6000)
     orng = po.RNG_PHILOX if rng == "philox" else po.RNG_MT
-    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="ref", rng=rng, rng_seed=0 if rng == "mt19937" else 12,
+    oorder = po.ORDER_REF if order == "ref" else po.ORDER_FAST
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order=order, rng=rng, rng_seed=0 if rng == "mt19937" else 12,
                       hoff_lookahead=True, trace=n_ev, **kw)) as sims:
         sims.run(n_ev)
         for r in range(n_rep):
-            o = po.Sim(po.default_opt(order=po.ORDER_REF, rng_mode=orng, seed=0 if rng == "mt19937" else 12, replica=r, n_events=n_ev,
+            o = po.Sim(po.default_opt(order=oorder, rng_mode=orng, seed=0 if rng == "mt19937" else 12, replica=r, n_events=n_ev,
                                       hoff_lookahead=1, **kw))
             status, done, tr = o.run(n_ev, trace=True)
             assert sims.read_status(r)[0] == status and done == n_ev
@@ -480,12 +482,28 @@ def test_handoff_lookahead_matches_the_oracle(rng, kw):
             assert_state_equal(sims.read_state(r), o.read())
             # the look-ahead did steer some decisions: the plain run of the same stream differs
             if r == 0:
-                p = po.Sim(po.default_opt(order=po.ORDER_REF, rng_mode=orng, seed=0 if rng == "mt19937" else 12, replica=r,
+                p = po.Sim(po.default_opt(order=oorder, rng_mode=orng, seed=0 if rng == "mt19937" else 12, replica=r,
                                           n_events=n_ev, **kw))
                 _, _, trp = p.run(n_ev, trace=True)
                 assert not np.array_equal(trp["ch"], tr["ch"])
-    with pytest.raises(DcaError):  # the FAST kernel has no look-ahead path
-        Replicas(Opt(n_events=10, order="fast", hoff_lookahead=True))
+
+
+def test_handoff_lookahead_fast_without_trace_and_in_chunks():
+    """The FAST look-ahead instantiation without a trace buffer, across unit boundaries (two launches, the second one
+    longer than a unit of dca_run_unit_events()) and on many replicas: final states equal the oracle's."""
+    from haskelldca_b200 import Opt, Replicas
+
+    n_rep, n_ev, kw = 40, 9000, dict(hoff_prob=0.4, call_rate=300.0)
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="fast", rng="philox", rng_seed=5, hoff_lookahead=True, **kw)) as sims:
+        sims.run(3000)
+        sims.run(6000)
+        assert (sims.read_summary()["status"] == po.SUCCESS).all()
+        for r in (0, 17, 39):
+            o = po.Sim(po.default_opt(order=po.ORDER_FAST, rng_mode=po.RNG_PHILOX, seed=5, replica=r, n_events=n_ev,
+                                      hoff_lookahead=1, **kw))
+            status, done, _ = o.run(n_ev)
+            assert status == po.SUCCESS and done == n_ev
+            assert_state_equal(sims.read_state(r), o.read())
 
 
 def test_units_of_a_launch_chain_correctly():

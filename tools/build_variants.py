@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from haskelldca_b200 import build as B
 
-KERNEL = "_ZN3dca4fast10k_run_fastILb0EEEvNS_7RunArgsE"
+KERNEL = "_ZN3dca4fast10k_run_fastILb0ELb0EEEvNS_7RunArgsE"
 for spec in sys.argv[1:]:
     name, _, flags = spec.partition("=")
     flags = [f for f in flags.split(",") if f]

@@ -3,7 +3,7 @@ the agents' event loop and their barrier 4, and between the event warp's loop he
 with the count of register moves / S2R / NOP -- what ptxas' register allocation added on top of the arithmetic.
 usage: loop_stats.py lib.so [...]"""
 import collections, re, subprocess, sys
-KERNEL = "_ZN3dca4fast10k_run_fastILb0EEEvNS_7RunArgsE"
+KERNEL = "_ZN3dca4fast10k_run_fastILb0ELb0EEEvNS_7RunArgsE"
 for lib in sys.argv[1:]:
     sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     body = sass.split("Function : " + KERNEL)[1].split("Function : ")[0]

@@ -1,7 +1,7 @@
 """Print the SASS of the agents' event loop (or the event warp's) of k_run_fast<false> in a built library, one instruction
 per line, for reading.  usage: sass_loop.py lib.so [agents|event]"""
 import re, subprocess, sys
-KERNEL = "_ZN3dca4fast10k_run_fastILb0EEEvNS_7RunArgsE"
+KERNEL = "_ZN3dca4fast10k_run_fastILb0ELb0EEEvNS_7RunArgsE"
 lib = sys.argv[1]
 which = sys.argv[2] if len(sys.argv) > 2 else "agents"
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
