@@ -883,7 +883,8 @@ __device__ __forceinline__ int argmax_last_warp(const float* q, const uint8_t* c
   // order-preserving map float -> uint32 (shifts and xors: no predicate latency), then two warp reductions
   const uint32_t bits = __float_as_uint(__fadd_rn(bq, 0.0f));                  // -0 -> +0
   uint32_t u = bits ^ ((uint32_t)((int32_t)bits >> 31) | 0x80000000u);         // negative: ~bits, else bits | sign
-  if (bq != bq) u = 0xFFFFFFFFu;    // above +inf: flags the uncommon path
+  // (a NaN flags the uncommon path by itself: the FADD above returns the canonical NaN 0x7FFFFFFF for any NaN input, which
+  //  this map sends to 0xFFFFFFFF, above +inf)
   if (lane >= n) u = 0u;
   const uint32_t m = __reduce_max_sync(0xffffffffu, u);
   const int key = __reduce_max_sync(0xffffffffu, (u == m) ? ((lane << 8) | cand_lane) : -1);
