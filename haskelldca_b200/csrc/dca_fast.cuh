@@ -33,6 +33,12 @@
 //            next event, statistics, stop rules -- barrier 4: publish (no wait) --
 //            push of the next event's new events
 //
+// Instantiations: k_run_fast<false> (the benchmarked one), <true> (parity trace / verify flags: one more barrier per event so
+// that the event warp sees the afterstate) and <true, true> (hand-off look-ahead, see q_lookahead; its own instantiation so
+// that the other two carry none of its code).  What bounds the kernel is the issue rate it sustains (66-68 % of the issue
+// slots, five CTAs sharing four schedulers): the number of instructions per event counts, not which warp executes them
+// (profiles/r2_v13_summary.md).
+//
 // The fp32 arithmetic is the FAST order specified in DESIGN.md ("Arithmetic
 // orders"; the CPU checker restates it independently): every operation is an explicit
 // round-to-nearest intrinsic, packed two lanes at a time (FFMA2 / FADD2) where
