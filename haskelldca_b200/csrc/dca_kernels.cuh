@@ -684,6 +684,112 @@ __device__ __forceinline__ void ref_dense_update(Smem& sm) {
   }
 }
 
+// ---- the run kernel's versions (k_run<ORDER_REF>): the same arithmetic, laid out for throughput ----
+// One lane's dense right fold in flatten order: of the products `p` of the current state when ch < 0 (V(s) on prod_w,
+// x.wGradCorr on prod_g), of the afterstate of candidate `ch` otherwise (the terms of ref_fold_candidate).  The code is the
+// same for every lane, so ALL folds of an event -- up to 30 candidates, V(s) and x.wGradCorr -- run in lock step on ONE
+// warp: an event then costs the issue slots of one fold (4 instructions per step against the 4-cycle FADD chain), and the
+// fold warps of the CTAs that share an SM sit on different schedulers (the hardware rotates the warp slots of
+// co-resident CTAs over the sub-partitions, tools/microbench/placement.cu).  Before: candidates on warp 0, the two plain
+// folds on warp 3, two CTAs per SM -> two fold warps per scheduler, 6.5 issue cycles per step.
+__device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* p, const int ch, const bool is_end) {
+  const RepState& s = sm.s;
+  const bool cand = ch >= 0;
+  const unsigned long long n4 = cand ? sm.t.n4mask : 0ULL, n2 = cand ? sm.t.n2mask : 0ULL;
+  const int cc = cand ? ch : 0;
+  const int diff = is_end ? -1 : 1;
+  const uint8_t want = is_end ? 1 : 0;
+  float acc = 0.0f;
+#pragma unroll 1
+  for (int cell = NCELL - 1; cell >= 0; --cell) {
+    const int pos = cell + (cell * 37 >> 8);  // (cell / 7) * 8 + cell % 7 for cell < 49
+    const float* pc = p + cell * NFEAT;
+    float t70 = pc[NCH];
+    if (((n2 >> cell) & 1ULL) && s.cnt2[cc * PLANE + pos] == want)  // Gridfuncs.hs:220-252
+      t70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] - diff), s.w[NCH * PLANE + pos]);
+    float tch = pc[cc];
+    if ((n4 >> cell) & 1ULL)                                        // Gridfuncs.hs:212-217
+      tch = __fmul_rn((float)((int)s.x[cc * PLANE + pos] + diff), s.w[cc * PLANE + pos]);
+    acc = __fadd_rn(t70, acc);
+#pragma unroll
+    for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {  // ten loads in flight, then ten dependent additions
+      float v[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) v[k] = pc[f0 + k];
+#pragma unroll
+      for (int k = 9; k >= 0; --k) acc = __fadd_rn((f0 + k) == ch ? tch : v[k], acc);
+    }
+  }
+  return acc;
+}
+// the folds of one event without look-ahead: warp 0 = candidates 0..29 (lanes 0..29), x.wGradCorr (lane 30), V(s) (lane 31);
+// warps 1.. = candidates 30.. (only the transient of the empty grid has that many)
+__device__ __forceinline__ void ref_folds(Smem& sm, const int n, const bool is_end) {
+  Scratch& t = sm.t;
+  const int wid = warp_id(), lane = lane_id();
+  const int k = wid == 0 ? (lane < 30 ? lane : -1) : 30 + 32 * (wid - 1) + lane;
+  const bool plain = wid == 0 && lane >= 30;
+  const bool is_cand = k >= 0 && k < n;
+  if (!(plain || is_cand)) return;
+  const float* p = (plain && lane == 30) ? t.prod_g : t.prod_w;
+  const float v = ref_fold_lane(sm, p, is_cand ? (int)t.cand[k] : -1, is_end);
+  if (is_cand) t.q[k] = v;
+  else if (lane == 30) t.dotg = v;
+  else t.val = v;
+}
+// The elementwise TDC update (ref_dense_update's arithmetic, operation for operation) by rows of the padded layout --
+// row (f, r) = eight bytes of frep, two 16-byte vectors of each weight array, no index arithmetic per element -- fused
+// with the products of the NEXT event (frep is in its afterstate when the update runs and nothing touches frep or the
+// weights until that event's folds).  UPDATE = false: the products alone (launch start).
+template <bool UPDATE>
+__device__ __forceinline__ void ref_update_rows(Smem& sm) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const float ctd = t.ctd, cavg = t.cavg, cdot = t.cdot, sg = t.sg;
+  const int act_ch = UPDATE ? t.act_ch : -1, diff = t.act_diff;
+  for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
+    const int f = row / ROWS, r = row - f * ROWS;
+    const int off = f * PLANE + r * ROWPAD;
+    const uint2 xn = *reinterpret_cast<const uint2*>(&s.x[off]);
+    uint2 xo = xn;
+    if (UPDATE && act_ch >= 0) {
+      if (f == act_ch) {  // x_old = x_new - diff on N4 \ {cell}
+        const uint2 m = t.n4b[r];
+        if (diff > 0) { xo.x -= m.x; xo.y -= m.y; } else { xo.x += m.x; xo.y += m.y; }
+      }
+      if (f == NCH) {     // n_elig: x_old = x_new + diff on the changed cells
+        const uint2 m = t.chgb[r];
+        if (diff > 0) { xo.x += m.x; xo.y += m.y; } else { xo.x -= m.x; xo.y -= m.y; }
+      }
+    }
+    float4 wa = *reinterpret_cast<const float4*>(&s.w[off]), wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
+    float4 ga = *reinterpret_cast<const float4*>(&s.wg[off]), gb = *reinterpret_cast<const float4*>(&s.wg[off + 4]);
+    float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+    float g[7] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z};
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+      const float xnf = byte_f(c < 4 ? xn.x : xn.y, c & 3);
+      if (UPDATE) {
+        const float xof = byte_f(c < 4 ? xo.x : xo.y, c & 3);
+        const float a1 = __fmul_rn(ctd, xof);
+        const float a3 = __fmul_rn(cdot, xnf);
+        const float gr = __fsub_rn(__fadd_rn(a1, cavg), a3);
+        w[c] = __fsub_rn(w[c], gr);
+        g[c] = __fadd_rn(g[c], __fmul_rn(sg, xof));
+      }
+      const int i = (r * COLS + c) * NFEAT + f;  // flatten order
+      t.prod_w[i] = __fmul_rn(xnf, w[c]);
+      t.prod_g[i] = __fmul_rn(xnf, g[c]);
+    }
+    if (UPDATE) {  // (the pad column goes back as it came)
+      *reinterpret_cast<float4*>(&s.w[off]) = make_float4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<float4*>(&s.w[off + 4]) = make_float4(w[4], w[5], w[6], wb.w);
+      *reinterpret_cast<float4*>(&s.wg[off]) = make_float4(g[0], g[1], g[2], g[3]);
+      *reinterpret_cast<float4*>(&s.wg[off + 4]) = make_float4(g[4], g[5], g[6], gb.w);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // hashes for parity traces (order-independent u64 sums); all threads
 // ---------------------------------------------------------------------------
@@ -803,20 +909,12 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     __syncthreads();
     const int n = t.ncand;
     const bool is_end = t.ev_is_end;
-    ref_products(sm);
-    __syncthreads();
+    // (the products of the current state are in place: formed at launch start and by every update since)
     const bool la = a.lookahead && is_end && n > 0 && s.ev_hoff != HOFF_NONE;  // uniform: the departure half of a hand-off
     if (la) {
       lookahead_folds(sm, n, t.ev_cell, s.ev_hoff);
     } else {
-      // candidates on threads 0..n-1, V(s) and x.wg on the last two threads
-      for (int k = threadIdx.x; k < n; k += nthreads - 2)
-        if (threadIdx.x < nthreads - 2) t.q[k] = ref_fold_candidate(sm, t.cand[k], is_end);
-      if (threadIdx.x >= nthreads - 2) {
-        const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : t.prod_g);
-        if (threadIdx.x == nthreads - 1) t.val = v;
-        else t.dotg = v;
-      }
+      ref_folds(sm, n, is_end);
       for (int k = threadIdx.x; k < n; k += nthreads) t.q_plain[k] = 0.0f;  // (unused without look-ahead)
     }
     if (threadIdx.x == 0) t.flag = la ? 1 : 0;
@@ -864,8 +962,8 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     }
   }
   __syncthreads();
-  // ---- accFn2's dense part: weight / gradient-correction update ----
-  ref_dense_update(sm);
+  // ---- accFn2's dense part: weight / gradient-correction update (and the next event's products) ----
+  ref_update_rows<true>(sm);
   if (TRACE) state_hashes(sm);
   __syncthreads();
   if (wid == 0) {
@@ -917,6 +1015,7 @@ __global__ void __launch_bounds__(128) k_run(RunArgs a) {
   if (!sm.s.initialized || sm.s.status != ST_RUNNING) return;  // uniform
   QRegs q{sm.s.n_end, sm.s.next_id, false};
   Rng rng = make_rng(a, sm.s, rep);
+  ref_update_rows<false>(sm);  // the products of the staged state (the barrier in front of the first folds covers them)
   for (long long it = 0; it < a.max_events; ++it) {
     run_event<ORDER, TRACE>(sm, a, q, rng, rep);
     if (sm.s.status != ST_RUNNING) break;  // uniform after the trailing barrier
