@@ -1318,6 +1318,14 @@ int dca_allreduce_stats(dca_handle** handles, int32_t n, int64_t out[10]) {
 extern "C" int dca_debug_cta(unsigned long long* out, int n_blocks) {
   return cudaMemcpyFromSymbol(out, dca::fast::g_cta, sizeof(unsigned long long) * 2 * (size_t)n_blocks) == cudaSuccess ? 0 : -1;
 }
+extern "C" int dca_debug_ref_phase(unsigned long long* out, int reset) {
+  if (cudaMemcpyFromSymbol(out, dca::g_ref_phase, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(dca::g_ref_phase, z, sizeof z);
+  }
+  return 0;
+}
 extern "C" int dca_debug_phase(unsigned long long* out, int reset) {
   if (cudaMemcpyFromSymbol(out, dca::fast::g_phase, sizeof(unsigned long long) * 48) != cudaSuccess) return -1;
   if (reset) {

@@ -23,6 +23,20 @@ namespace dca {
 
 __constant__ Tables c_tab;
 
+#ifdef DCA_PHASE_CLOCK  // development only: cycles per phase of the REF-order run kernel, summed over CTAs and events
+__device__ unsigned long long g_ref_phase[8];
+#define DCA_RCLK(i)                                                              \
+  if (threadIdx.x == 0) {                                                        \
+    const unsigned now_ = (unsigned)clock64();                                   \
+    atomicAdd(&g_ref_phase[i], (unsigned long long)(now_ - rclk_));              \
+    rclk_ = now_;                                                                \
+  }
+#define DCA_RCLK_START unsigned rclk_ = (unsigned)clock64();
+#else
+#define DCA_RCLK(i)
+#define DCA_RCLK_START
+#endif
+
 struct RunArgs {
   RepState* states;
   int n_replicas;
@@ -692,6 +706,35 @@ __device__ __forceinline__ void ref_dense_update(Smem& sm) {
 // fold warps of the CTAs that share an SM sit on different schedulers (the hardware rotates the warp slots of
 // co-resident CTAs over the sub-partitions, tools/microbench/placement.cu).  Before: candidates on warp 0, the two plain
 // folds on warp 3, two CTAs per SM -> two fold warps per scheduler, 6.5 issue cycles per step.
+// The schedule is explicit (volatile asm keeps the order): a term is selected -- `f == ch ? re-formed : product` -- one batch
+// of ten AHEAD of its addition, so that the only dependence an addition waits for is the previous addition (ptxas, left
+// alone, puts every select two instructions in front of its FADD and the fold runs at 9 cycles per term instead of 4-5).
+__device__ __forceinline__ float ref_sel(const float v, const float tch, const int ch, const int f) {
+  float u;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\tselp.f32 %0, %4, %1, p;\n\t}" : "=f"(u) : "f"(v), "r"(ch), "r"(f), "f"(tch));
+  return u;
+}
+__device__ __forceinline__ void ref_add(float& acc, const float u) {
+  asm volatile("add.rn.f32 %0, %1, %0;" : "+f"(acc) : "f"(u));
+}
+struct RefCellTerms {  // the two terms of a cell that candidate `ch` may change
+  float t70, tch;
+};
+__device__ __forceinline__ RefCellTerms ref_cell_terms(const RepState& s, const float* pc, const int cell, const int cc,
+                                                       const unsigned long long n4, const unsigned long long n2,
+                                                       const int diff, const uint8_t want) {
+  const int pos = cell + (cell * 37 >> 8);  // (cell / 7) * 8 + cell % 7 for cell < 49
+  RefCellTerms r;
+  // branch-free: both re-formed products are always computed, a select keeps the current state's where nothing changes
+  const float r70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] - diff), s.w[NCH * PLANE + pos]);  // Gridfuncs.hs:220-252
+  const float rch = __fmul_rn((float)((int)s.x[cc * PLANE + pos] + diff), s.w[cc * PLANE + pos]);    // Gridfuncs.hs:212-217
+  const uint8_t c2 = s.cnt2[cc * PLANE + pos];
+  const bool c70 = (((n2 >> cell) & 1ULL) != 0) & (c2 == want);
+  const bool cch = (n4 >> cell) & 1ULL;
+  r.t70 = c70 ? r70 : pc[NCH];
+  r.tch = cch ? rch : pc[cc];
+  return r;
+}
 __device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* p, const int ch, const bool is_end) {
   const RepState& s = sm.s;
   const bool cand = ch >= 0;
@@ -699,26 +742,39 @@ __device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* p, cons
   const int cc = cand ? ch : 0;
   const int diff = is_end ? -1 : 1;
   const uint8_t want = is_end ? 1 : 0;
+  static_assert(NCH % 10 == 0, "the fold handles ten terms at a time");
   float acc = 0.0f;
+  const float* pc = p + (NCELL - 1) * NFEAT;
+  RefCellTerms ct = ref_cell_terms(s, pc, NCELL - 1, cc, n4, n2, diff, want);
+  float u[10];  // the selected terms of the batch that is added next
+#pragma unroll
+  for (int k = 0; k < 10; ++k) u[k] = ref_sel(pc[NCH - 10 + k], ct.tch, ch, NCH - 10 + k);
 #pragma unroll 1
   for (int cell = NCELL - 1; cell >= 0; --cell) {
-    const int pos = cell + (cell * 37 >> 8);  // (cell / 7) * 8 + cell % 7 for cell < 49
-    const float* pc = p + cell * NFEAT;
-    float t70 = pc[NCH];
-    if (((n2 >> cell) & 1ULL) && s.cnt2[cc * PLANE + pos] == want)  // Gridfuncs.hs:220-252
-      t70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] - diff), s.w[NCH * PLANE + pos]);
-    float tch = pc[cc];
-    if ((n4 >> cell) & 1ULL)                                        // Gridfuncs.hs:212-217
-      tch = __fmul_rn((float)((int)s.x[cc * PLANE + pos] + diff), s.w[cc * PLANE + pos]);
-    acc = __fadd_rn(t70, acc);
+    // the next cell's two terms (cell 0: its own again, unused), in flight while this cell's 71 terms are added
+    const int celln = cell > 0 ? cell - 1 : 0;
+    const float* pn = p + celln * NFEAT;
+    const RefCellTerms cn = ref_cell_terms(s, pn, celln, cc, n4, n2, diff, want);
+    ref_add(acc, ct.t70);
 #pragma unroll
-    for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {  // ten loads in flight, then ten dependent additions
-      float v[10];
+    for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {
+      // the batch below (the top batch of the next cell after the last one), selected while this one is added
+      const float* q = f0 > 0 ? pc + (f0 - 10) : pn + (NCH - 10);
+      const int fq = f0 > 0 ? f0 - 10 : NCH - 10;
+      const float tq = f0 > 0 ? ct.tch : cn.tch;
+      float v[10], un[10];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) v[k] = pc[f0 + k];
+      for (int k = 0; k < 10; ++k) v[k] = q[k];
 #pragma unroll
-      for (int k = 9; k >= 0; --k) acc = __fadd_rn((f0 + k) == ch ? tch : v[k], acc);
+      for (int k = 9; k >= 0; --k) {
+        ref_add(acc, u[k]);
+        un[k] = ref_sel(v[k], tq, ch, fq + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) u[k] = un[k];
     }
+    ct = cn;
+    pc = pn;
   }
   return acc;
 }
@@ -883,6 +939,7 @@ __device__ __forceinline__ Rng make_rng(const RunArgs& a, const RepState& s, int
 template <int ORDER, bool TRACE>
 __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, Rng& rng,
                                           int rep) {
+  DCA_RCLK_START
   RepState& s = sm.s;
   Scratch& t = sm.t;
   const int wid = warp_id(), lane = lane_id();
@@ -907,6 +964,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
   }
   {
     __syncthreads();
+    DCA_RCLK(0)
     const int n = t.ncand;
     const bool is_end = t.ev_is_end;
     // (the products of the current state are in place: formed at launch start and by every update since)
@@ -919,6 +977,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     }
     if (threadIdx.x == 0) t.flag = la ? 1 : 0;
     __syncthreads();
+    DCA_RCLK(1)
   }
   if (wid == 0) {
     const int n = t.ncand, cell = t.ev_cell;
@@ -962,10 +1021,12 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     }
   }
   __syncthreads();
+  DCA_RCLK(2)
   // ---- accFn2's dense part: weight / gradient-correction update (and the next event's products) ----
   ref_update_rows<true>(sm);
   if (TRACE) state_hashes(sm);
   __syncthreads();
+  DCA_RCLK(3)
   if (wid == 0) {
     int stop = t.stop;
     if (stop == ST_RUNNING && (a.verify_rc || a.verify_nb)) {
@@ -998,6 +1059,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     }
   }
   __syncthreads();
+  DCA_RCLK(4)
 }
 
 // ---------------------------------------------------------------------------
