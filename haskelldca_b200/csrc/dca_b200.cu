@@ -429,7 +429,7 @@ int dca_create(const dca_config* cfg, dca_handle** out) {
       (rc = set_smem(h, fast::k_run_fast<true>, sizeof(fast::SmemF))) ||
       (rc = set_smem(h, fast::k_run_fast<true, true>, sizeof(fast::SmemLA))) ||
       (rc = set_smem(h, fast::k_step_fast, sizeof(fast::SmemF))) ||
-      (rc = set_smem(h, k_run<ORDER_REF, false>)) || (rc = set_smem(h, k_run<ORDER_REF, true>)) ||
+      (rc = set_smem(h, k_run<ORDER_REF, false>, SMEM_RUN_BYTES)) || (rc = set_smem(h, k_run<ORDER_REF, true>, SMEM_RUN_BYTES)) ||
       (rc = set_smem(h, k_step<ORDER_REF>)) || (rc = set_smem(h, k_gf_violates)))
     return bail(rc);
   CKB(cudaMalloc(&h->d_units, sizeof(unsigned) * (size_t)h->n));
@@ -550,7 +550,7 @@ int dca_run_async(dca_handle* h, int64_t max_events) {
   // (the TRACE instantiation of the fused FAST kernel also serves the verify flags: it has the extra per-event barrier)
   const bool trace_fast = trace || a.verify_rc || a.verify_nb;
   const dim3 grid(h->n), block(128);
-  const size_t smem = sizeof(Smem);
+  const size_t smem = SMEM_RUN_BYTES;  // (REF-order run kernel: RepState + Scratch without the step kernel's prod_g)
   CK(cudaEventRecord(h->ev0, h->stream));
   if (h->cfg.order == DCA_ORDER_FAST) {
     // one CTA per unit (replica, chunk of kFastChunkEvents events), numbered chunk-major

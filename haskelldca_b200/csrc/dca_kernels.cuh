@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <cstddef>
 
 #include "dca_state.h"
 
@@ -78,19 +79,25 @@ struct Scratch {
   // formed by all threads once per event: every dense right fold of the event (V(s), x.wGradCorr, one per candidate)
   // then reads them as broadcasts and only re-forms the <= 61 terms its afterstate changes
   float prod_w[NFEAT * NCELL + 1];
-  float prod_g[NFEAT * NCELL + 1];
   // hand-off look-ahead (extension): the (channel to free, channel to assign in the target cell) pairs of one round
   float q_plain[72];           // V(afterstate_k): the TD target stays the real next state
   float pair_q[LA_PAIRS];
   uint8_t pair_k[LA_PAIRS];    // index into cand
   uint8_t pair_h[LA_PAIRS];    // channel in the target cell, LA_NONE = the plain afterstate of the END
   int la_npairs, la_knext;
+  // LAST: the step kernel's products with wGradCorr.  The run kernel does not allocate this array: it keeps wGradCorr
+  // itself in global memory (only the elementwise update touches it, one coalesced read and write per event, served by
+  // L2) and the products in the shared-memory bytes of RepState::wg -- 72 KB instead of 86 KB per CTA, three CTAs per SM
+  float prod_g[NFEAT * NCELL + 1];
 };
 
 struct Smem {
   RepState s;
   Scratch t;
 };
+// shared memory of the run kernel: everything up to Scratch::prod_g
+constexpr size_t SMEM_RUN_BYTES = (offsetof(Smem, t) + offsetof(Scratch, prod_g) + 15) / 16 * 16;
+static_assert(sizeof(((RepState*)0)->wg) >= sizeof(float) * (NFEAT * NCELL + 1), "the run kernel's products live in RepState::wg");
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -599,7 +606,7 @@ __device__ __noinline__ float ref_fold_two(const Smem& sm, const int cell1, cons
 }
 
 // the look-ahead values of all candidates of a hand-off END: t.q[k] (selection) and t.q_plain[k] (TD target).  All threads.
-__device__ __forceinline__ void lookahead_folds(Smem& sm, const int n, const int cell1, const int cell2) {
+__device__ __forceinline__ void lookahead_folds(Smem& sm, const int n, const int cell1, const int cell2, const float* prod_g) {
   RepState& s = sm.s;
   Scratch& t = sm.t;
   const int lane = lane_id(), wid = warp_id(), nthreads = blockDim.x;
@@ -646,7 +653,7 @@ __device__ __forceinline__ void lookahead_folds(Smem& sm, const int n, const int
         t.pair_q[p] = ref_fold_two(sm, cell1, t.cand[t.pair_k[p]], cell2, h == LA_NONE ? -1 : h);
       }
     } else if (first_round) {  // V(s) and x.wGradCorr of the current state, once
-      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : t.prod_g);
+      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : prod_g);
       if (threadIdx.x == nthreads - 1) t.val = v;
       else t.dotg = v;
     }
@@ -780,14 +787,14 @@ __device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* p, cons
 }
 // the folds of one event without look-ahead: warp 0 = candidates 0..29 (lanes 0..29), x.wGradCorr (lane 30), V(s) (lane 31);
 // warps 1.. = candidates 30.. (only the transient of the empty grid has that many)
-__device__ __forceinline__ void ref_folds(Smem& sm, const int n, const bool is_end) {
+__device__ __forceinline__ void ref_folds(Smem& sm, const int n, const bool is_end, const float* prod_g) {
   Scratch& t = sm.t;
   const int wid = warp_id(), lane = lane_id();
   const int k = wid == 0 ? (lane < 30 ? lane : -1) : 30 + 32 * (wid - 1) + lane;
   const bool plain = wid == 0 && lane >= 30;
   const bool is_cand = k >= 0 && k < n;
   if (!(plain || is_cand)) return;
-  const float* p = (plain && lane == 30) ? t.prod_g : t.prod_w;
+  const float* p = (plain && lane == 30) ? prod_g : t.prod_w;
   const float v = ref_fold_lane(sm, p, is_cand ? (int)t.cand[k] : -1, is_end);
   if (is_cand) t.q[k] = v;
   else if (lane == 30) t.dotg = v;
@@ -798,12 +805,27 @@ __device__ __forceinline__ void ref_folds(Smem& sm, const int n, const bool is_e
 // with the products of the NEXT event (frep is in its afterstate when the update runs and nothing touches frep or the
 // weights until that event's folds).  UPDATE = false: the products alone (launch start).
 template <bool UPDATE>
-__device__ __forceinline__ void ref_update_rows(Smem& sm) {
+__device__ __forceinline__ void ref_update_rows(Smem& sm, RepState* gs, float* prod_g) {
   RepState& s = sm.s;
   Scratch& t = sm.t;
   const float ctd = t.ctd, cavg = t.cavg, cdot = t.cdot, sg = t.sg;
   const int act_ch = UPDATE ? t.act_ch : -1, diff = t.act_diff;
-  for (int row = threadIdx.x; row < NROW; row += blockDim.x) {
+  constexpr int NIT = (NROW + 127) / 128;  // rows per thread (the run kernel has 128 threads)
+  // wGradCorr lives in global memory: all of this thread's rows are requested before the first one is used
+  float4 ga[NIT], gb[NIT];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int row = (int)threadIdx.x + 128 * it;
+    if (row < NROW) {
+      const int f = row / ROWS, off = f * PLANE + (row - f * ROWS) * ROWPAD;
+      ga[it] = *reinterpret_cast<const float4*>(&gs->wg[off]);
+      gb[it] = *reinterpret_cast<const float4*>(&gs->wg[off + 4]);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int row = (int)threadIdx.x + 128 * it;
+    if (row >= NROW) break;
     const int f = row / ROWS, r = row - f * ROWS;
     const int off = f * PLANE + r * ROWPAD;
     const uint2 xn = *reinterpret_cast<const uint2*>(&s.x[off]);
@@ -819,9 +841,8 @@ __device__ __forceinline__ void ref_update_rows(Smem& sm) {
       }
     }
     float4 wa = *reinterpret_cast<const float4*>(&s.w[off]), wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
-    float4 ga = *reinterpret_cast<const float4*>(&s.wg[off]), gb = *reinterpret_cast<const float4*>(&s.wg[off + 4]);
     float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
-    float g[7] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z};
+    float g[7] = {ga[it].x, ga[it].y, ga[it].z, ga[it].w, gb[it].x, gb[it].y, gb[it].z};
 #pragma unroll
     for (int c = 0; c < COLS; ++c) {
       const float xnf = byte_f(c < 4 ? xn.x : xn.y, c & 3);
@@ -835,13 +856,13 @@ __device__ __forceinline__ void ref_update_rows(Smem& sm) {
       }
       const int i = (r * COLS + c) * NFEAT + f;  // flatten order
       t.prod_w[i] = __fmul_rn(xnf, w[c]);
-      t.prod_g[i] = __fmul_rn(xnf, g[c]);
+      prod_g[i] = __fmul_rn(xnf, g[c]);
     }
     if (UPDATE) {  // (the pad column goes back as it came)
       *reinterpret_cast<float4*>(&s.w[off]) = make_float4(w[0], w[1], w[2], w[3]);
       *reinterpret_cast<float4*>(&s.w[off + 4]) = make_float4(w[4], w[5], w[6], wb.w);
-      *reinterpret_cast<float4*>(&s.wg[off]) = make_float4(g[0], g[1], g[2], g[3]);
-      *reinterpret_cast<float4*>(&s.wg[off + 4]) = make_float4(g[4], g[5], g[6], gb.w);
+      *reinterpret_cast<float4*>(&gs->wg[off]) = make_float4(g[0], g[1], g[2], g[3]);
+      *reinterpret_cast<float4*>(&gs->wg[off + 4]) = make_float4(g[4], g[5], g[6], gb[it].w);
     }
   }
 }
@@ -913,6 +934,23 @@ __device__ __forceinline__ void stage_out(const Smem& sm, RepState* g) {
   for (int i = threadIdx.x; i < (int)(sizeof(RepState) / 16); i += blockDim.x) dst[i] = src[i];
 }
 
+// the run kernel's staging: everything but wGradCorr, which stays in global memory (its shared-memory bytes hold products)
+static_assert(offsetof(RepState, wg) % 16 == 0 && offsetof(RepState, x) % 16 == 0, "RepState::wg is a 16-byte aligned range");
+__device__ __forceinline__ void stage_in_run(Smem& sm, const RepState* g) {
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  uint4* dst = reinterpret_cast<uint4*>(&sm.s);
+  constexpr int A = (int)(offsetof(RepState, wg) / 16), B = (int)(offsetof(RepState, x) / 16), N = (int)(sizeof(RepState) / 16);
+  for (int i = threadIdx.x; i < A; i += blockDim.x) dst[i] = src[i];
+  for (int i = B + threadIdx.x; i < N; i += blockDim.x) dst[i] = src[i];
+}
+__device__ __forceinline__ void stage_out_run(const Smem& sm, RepState* g) {
+  const uint4* src = reinterpret_cast<const uint4*>(&sm.s);
+  uint4* dst = reinterpret_cast<uint4*>(g);
+  constexpr int A = (int)(offsetof(RepState, wg) / 16), B = (int)(offsetof(RepState, x) / 16), N = (int)(sizeof(RepState) / 16);
+  for (int i = threadIdx.x; i < A; i += blockDim.x) dst[i] = src[i];
+  for (int i = B + threadIdx.x; i < N; i += blockDim.x) dst[i] = src[i];
+}
+
 __device__ __forceinline__ Rng make_rng(const RunArgs& a, const RepState& s, int rep) {
   Rng rng;
   rng.mode = a.rng_mode;
@@ -938,7 +976,7 @@ __device__ __forceinline__ Rng make_rng(const RunArgs& a, const RepState& s, int
 // ---------------------------------------------------------------------------
 template <int ORDER, bool TRACE>
 __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, Rng& rng,
-                                          int rep) {
+                                          int rep, RepState* gs, float* prod_g) {
   DCA_RCLK_START
   RepState& s = sm.s;
   Scratch& t = sm.t;
@@ -970,9 +1008,9 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     // (the products of the current state are in place: formed at launch start and by every update since)
     const bool la = a.lookahead && is_end && n > 0 && s.ev_hoff != HOFF_NONE;  // uniform: the departure half of a hand-off
     if (la) {
-      lookahead_folds(sm, n, t.ev_cell, s.ev_hoff);
+      lookahead_folds(sm, n, t.ev_cell, s.ev_hoff, prod_g);
     } else {
-      ref_folds(sm, n, is_end);
+      ref_folds(sm, n, is_end, prod_g);
       for (int k = threadIdx.x; k < n; k += nthreads) t.q_plain[k] = 0.0f;  // (unused without look-ahead)
     }
     if (threadIdx.x == 0) t.flag = la ? 1 : 0;
@@ -1023,7 +1061,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
   __syncthreads();
   DCA_RCLK(2)
   // ---- accFn2's dense part: weight / gradient-correction update (and the next event's products) ----
-  ref_update_rows<true>(sm);
+  ref_update_rows<true>(sm, gs, prod_g);
   if (TRACE) state_hashes(sm);
   __syncthreads();
   DCA_RCLK(3)
@@ -1066,20 +1104,21 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
 // The fused run kernel: dca_run.  grid = n_replicas CTAs.
 // ---------------------------------------------------------------------------
 template <int ORDER, bool TRACE>
-__global__ void __launch_bounds__(128) k_run(RunArgs a) {
+__global__ void __launch_bounds__(128, 3) k_run(RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int rep = blockIdx.x;
   if (rep >= a.n_replicas) return;
   RepState* g = a.states + rep;
-  stage_in(sm, g);
+  stage_in_run(sm, g);
   __syncthreads();
   if (!sm.s.initialized || sm.s.status != ST_RUNNING) return;  // uniform
   QRegs q{sm.s.n_end, sm.s.next_id, false};
   Rng rng = make_rng(a, sm.s, rep);
-  ref_update_rows<false>(sm);  // the products of the staged state (the barrier in front of the first folds covers them)
+  float* const prod_g = sm.s.wg;  // wGradCorr itself stays in global memory (see Scratch::prod_g)
+  ref_update_rows<false>(sm, g, prod_g);  // the products of the staged state (the barrier in front of the first folds covers them)
   for (long long it = 0; it < a.max_events; ++it) {
-    run_event<ORDER, TRACE>(sm, a, q, rng, rep);
+    run_event<ORDER, TRACE>(sm, a, q, rng, rep, g, prod_g);
     if (sm.s.status != ST_RUNNING) break;  // uniform after the trailing barrier
   }
   if (threadIdx.x == 0) {
@@ -1088,7 +1127,7 @@ __global__ void __launch_bounds__(128) k_run(RunArgs a) {
     sm.s.ndraws = rng.ndraws;
   }
   __syncthreads();
-  stage_out(sm, g);
+  stage_out_run(sm, g);
 }
 
 // ---------------------------------------------------------------------------
