@@ -66,6 +66,7 @@ struct Scratch {
   uint2 n4b[8];    // row byte masks: N4(cell) \ {cell}
   uint2 n2b[8];    // row byte masks: N2(cell) u {cell}
   uint2 chgb[8];   // row byte masks: cells whose n_elig changes (chosen action)
+  uint2 n4b_upd[8];  // n4b of the event whose update is running (the run kernel builds the next event's masks meanwhile)
   unsigned long long n4mask, n2mask, chgmask;
   unsigned long long hash_grid, hash_frep;
   float ctd, cavg, cdot, sg;   // TDC scalars of this event
@@ -804,65 +805,69 @@ __device__ __forceinline__ void ref_folds(Smem& sm, const int n, const bool is_e
 // row (f, r) = eight bytes of frep, two 16-byte vectors of each weight array, no index arithmetic per element -- fused
 // with the products of the NEXT event (frep is in its afterstate when the update runs and nothing touches frep or the
 // weights until that event's folds).  UPDATE = false: the products alone (launch start).
-template <bool UPDATE>
-__device__ __forceinline__ void ref_update_rows(Smem& sm, RepState* gs, float* prod_g) {
+template <bool UPDATE, int NT>
+__device__ __forceinline__ void ref_update_rows(Smem& sm, RepState* gs, float* prod_g, const int tid) {
   RepState& s = sm.s;
   Scratch& t = sm.t;
   const float ctd = t.ctd, cavg = t.cavg, cdot = t.cdot, sg = t.sg;
   const int act_ch = UPDATE ? t.act_ch : -1, diff = t.act_diff;
-  constexpr int NIT = (NROW + 127) / 128;  // rows per thread (the run kernel has 128 threads)
-  // wGradCorr lives in global memory: all of this thread's rows are requested before the first one is used
-  float4 ga[NIT], gb[NIT];
+  constexpr int NIT = (NROW + NT - 1) / NT;   // rows per thread
+  constexpr int CH = NT >= 128 ? 4 : 3;       // rows whose wGradCorr is requested together
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int row = (int)threadIdx.x + 128 * it;
-    if (row < NROW) {
-      const int f = row / ROWS, off = f * PLANE + (row - f * ROWS) * ROWPAD;
-      ga[it] = *reinterpret_cast<const float4*>(&gs->wg[off]);
-      gb[it] = *reinterpret_cast<const float4*>(&gs->wg[off + 4]);
-    }
-  }
+  for (int it0 = 0; it0 < NIT; it0 += CH) {
+    // wGradCorr lives in global memory: the rows of a chunk are requested before the first one is used
+    float4 ga[CH], gb[CH];
 #pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int row = (int)threadIdx.x + 128 * it;
-    if (row >= NROW) break;
-    const int f = row / ROWS, r = row - f * ROWS;
-    const int off = f * PLANE + r * ROWPAD;
-    const uint2 xn = *reinterpret_cast<const uint2*>(&s.x[off]);
-    uint2 xo = xn;
-    if (UPDATE && act_ch >= 0) {
-      if (f == act_ch) {  // x_old = x_new - diff on N4 \ {cell}
-        const uint2 m = t.n4b[r];
-        if (diff > 0) { xo.x -= m.x; xo.y -= m.y; } else { xo.x += m.x; xo.y += m.y; }
-      }
-      if (f == NCH) {     // n_elig: x_old = x_new + diff on the changed cells
-        const uint2 m = t.chgb[r];
-        if (diff > 0) { xo.x += m.x; xo.y += m.y; } else { xo.x -= m.x; xo.y -= m.y; }
+    for (int j = 0; j < CH; ++j) {
+      const int row = tid + NT * (it0 + j);
+      if (it0 + j < NIT && row < NROW) {
+        const int f = row / ROWS, off = f * PLANE + (row - f * ROWS) * ROWPAD;
+        ga[j] = *reinterpret_cast<const float4*>(&gs->wg[off]);
+        gb[j] = *reinterpret_cast<const float4*>(&gs->wg[off + 4]);
       }
     }
-    float4 wa = *reinterpret_cast<const float4*>(&s.w[off]), wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
-    float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
-    float g[7] = {ga[it].x, ga[it].y, ga[it].z, ga[it].w, gb[it].x, gb[it].y, gb[it].z};
 #pragma unroll
-    for (int c = 0; c < COLS; ++c) {
-      const float xnf = byte_f(c < 4 ? xn.x : xn.y, c & 3);
-      if (UPDATE) {
-        const float xof = byte_f(c < 4 ? xo.x : xo.y, c & 3);
-        const float a1 = __fmul_rn(ctd, xof);
-        const float a3 = __fmul_rn(cdot, xnf);
-        const float gr = __fsub_rn(__fadd_rn(a1, cavg), a3);
-        w[c] = __fsub_rn(w[c], gr);
-        g[c] = __fadd_rn(g[c], __fmul_rn(sg, xof));
+    for (int j = 0; j < CH; ++j) {
+      const int row = tid + NT * (it0 + j);
+      if (it0 + j >= NIT || row >= NROW) break;
+      const int f = row / ROWS, r = row - f * ROWS;
+      const int off = f * PLANE + r * ROWPAD;
+      const uint2 xn = *reinterpret_cast<const uint2*>(&s.x[off]);
+      uint2 xo = xn;
+      if (UPDATE && act_ch >= 0) {
+        if (f == act_ch) {  // x_old = x_new - diff on N4 \ {cell}
+          const uint2 m = t.n4b_upd[r];
+          if (diff > 0) { xo.x -= m.x; xo.y -= m.y; } else { xo.x += m.x; xo.y += m.y; }
+        }
+        if (f == NCH) {     // n_elig: x_old = x_new + diff on the changed cells
+          const uint2 m = t.chgb[r];
+          if (diff > 0) { xo.x += m.x; xo.y += m.y; } else { xo.x -= m.x; xo.y -= m.y; }
+        }
       }
-      const int i = (r * COLS + c) * NFEAT + f;  // flatten order
-      t.prod_w[i] = __fmul_rn(xnf, w[c]);
-      prod_g[i] = __fmul_rn(xnf, g[c]);
-    }
-    if (UPDATE) {  // (the pad column goes back as it came)
-      *reinterpret_cast<float4*>(&s.w[off]) = make_float4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<float4*>(&s.w[off + 4]) = make_float4(w[4], w[5], w[6], wb.w);
-      *reinterpret_cast<float4*>(&gs->wg[off]) = make_float4(g[0], g[1], g[2], g[3]);
-      *reinterpret_cast<float4*>(&gs->wg[off + 4]) = make_float4(g[4], g[5], g[6], gb[it].w);
+      float4 wa = *reinterpret_cast<const float4*>(&s.w[off]), wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
+      float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+      float g[7] = {ga[j].x, ga[j].y, ga[j].z, ga[j].w, gb[j].x, gb[j].y, gb[j].z};
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) {
+        const float xnf = byte_f(c < 4 ? xn.x : xn.y, c & 3);
+        if (UPDATE) {
+          const float xof = byte_f(c < 4 ? xo.x : xo.y, c & 3);
+          const float a1 = __fmul_rn(ctd, xof);
+          const float a3 = __fmul_rn(cdot, xnf);
+          const float gr = __fsub_rn(__fadd_rn(a1, cavg), a3);
+          w[c] = __fsub_rn(w[c], gr);
+          g[c] = __fadd_rn(g[c], __fmul_rn(sg, xof));
+        }
+        const int i = (r * COLS + c) * NFEAT + f;  // flatten order
+        t.prod_w[i] = __fmul_rn(xnf, w[c]);
+        prod_g[i] = __fmul_rn(xnf, g[c]);
+      }
+      if (UPDATE) {  // (the pad column goes back as it came)
+        *reinterpret_cast<float4*>(&s.w[off]) = make_float4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<float4*>(&s.w[off + 4]) = make_float4(w[4], w[5], w[6], wb.w);
+        *reinterpret_cast<float4*>(&gs->wg[off]) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(&gs->wg[off + 4]) = make_float4(g[4], g[5], g[6], gb[j].w);
+      }
     }
   }
 }
@@ -1058,10 +1063,11 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
       t.stop = stop;
     }
   }
+  if (threadIdx.x < 8) t.n4b_upd[threadIdx.x] = t.n4b[threadIdx.x];
   __syncthreads();
   DCA_RCLK(2)
   // ---- accFn2's dense part: weight / gradient-correction update (and the next event's products) ----
-  ref_update_rows<true>(sm, gs, prod_g);
+  ref_update_rows<true, 128>(sm, gs, prod_g, (int)threadIdx.x);
   if (TRACE) state_hashes(sm);
   __syncthreads();
   DCA_RCLK(3)
@@ -1101,6 +1107,109 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
 }
 
 // ---------------------------------------------------------------------------
+// The event loop of the run kernel without the parity trace: the same steps as run_event, arranged so that the
+// event-sequential tail of an event runs NEXT TO its dense update instead of in front of it.  Once the decision and
+// the TD scalars are published, warps 1-3 run the update (and form the next event's products) while warp 0 runs
+// environmentStep, the stop rules and the next event's candidate list -- none of which reads the weights.  Three CTA
+// barriers per event instead of five.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ref_prepare_event(Smem& sm) {  // warp 0: candidates and masks of the current event
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const int cell = s.ev_cell;
+  const bool is_end = s.ev_type == EV_END;
+  const int n = build_candidates(sm, cell, is_end);
+  if (lane_id() == 0) {
+    t.ncand = n;
+    t.ev_cell = cell;
+    t.ev_is_end = is_end;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a, QRegs& q, Rng& rng, RepState* gs,
+                                                      float* prod_g) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const int wid = warp_id(), lane = lane_id();
+  if (wid == 0) ref_prepare_event(sm);
+  DCA_RCLK_START
+  for (long long it = 0;; ++it) {
+    __syncthreads();  // the event's candidates, the products of its state and the status word are published
+    DCA_RCLK(3)
+    if (it >= a.max_events || s.status != ST_RUNNING) break;  // uniform
+    const int n = t.ncand;
+    const bool is_end = t.ev_is_end;
+    const bool la = a.lookahead && is_end && n > 0 && s.ev_hoff != HOFF_NONE;  // uniform: the departure half of a hand-off
+    if (la) lookahead_folds(sm, n, t.ev_cell, s.ev_hoff, prod_g);
+    else ref_folds(sm, n, is_end, prod_g);
+    __syncthreads();
+    DCA_RCLK(1)
+    int act = -1;
+    if (wid == 0) {
+      const int cell = t.ev_cell;
+      const float val = t.val, dotg = t.dotg;
+      float next_val = val;  // no action: nextFrep = frep (Simulator.hs:170-171)
+      if (n > 0) {
+        const int k = argmax_last(t.q, n);  // selectAction, Simulator.hs:202
+        act = t.cand[k];
+        next_val = la ? t.q_plain[k] : t.q[k];  // (look-ahead only steers the selection: nextFrep is the real afterstate)
+        const unsigned long long chg = elig_change_mask(s, act, is_end, t.n2mask);
+        apply_action(sm, cell, is_end, act, chg);  // gridStep, Simulator.hs:137-144
+      }
+      // backward scalars (Agent.hs:62-67,75,78)
+      const float avgR = s.avg_reward;
+      const float reward = (float)s.ncalls;  // boolSum nextGrid
+      const float td = __fsub_rn(__fadd_rn(__fsub_rn(reward, avgR), next_val), val);
+      const float c = __fmul_rn(-2.0f, s.alpha_net);
+      if (lane < 8) t.n4b_upd[lane] = t.n4b[lane];
+      if (lane == 0) {
+        t.ctd = __fmul_rn(c, td);
+        t.cavg = __fmul_rn(c, avgR);
+        t.cdot = __fmul_rn(c, dotg);
+        t.sg = __fmul_rn(s.alpha_grad, __fsub_rn(td, dotg));
+        t.act_ch = act;
+        t.act_diff = is_end ? -1 : 1;
+        t.loss = td;
+        s.avg_reward = __fadd_rn(avgR, __fmul_rn(s.alpha_avg, td));
+      }
+    }
+    __syncthreads();  // the decision and the scalars of the update are published
+    DCA_RCLK(2)
+    if (wid == 0) {
+      environment_step(s, q, rng, act);  // Simulator.hs:101-134
+      int stop = ST_RUNNING;
+      if (lane == 0) {
+        const float td = t.loss;
+        s.iter += 1;  // Simulator.hs:131
+        // stop rules of runPeriod (SimRunner.hs:150-169), in the reference's order
+        if (td != td) stop = ST_NAN_LOSS;
+        else {
+          s.loss_sum = __fadd_rn(s.loss_sum, td);
+          s.loss_n += 1;
+        }
+        if (stop == ST_RUNNING && q.overflow) stop = ST_QUEUE_OVERFLOW;
+      }
+      stop = __shfl_sync(0xffffffffu, stop, 0);
+      if (stop == ST_RUNNING && (a.verify_rc || a.verify_nb)) {
+        const int v = verify_state(sm, a.verify_rc, a.verify_nb);
+        if (v) stop = v;
+      }
+      if (lane == 0) {
+        if (stop == ST_RUNNING && s.min_loss > 0.0f && s.iter > 50 && fabsf(t.loss) < s.min_loss) stop = ST_ZERO_LOSS;
+        if (stop == ST_RUNNING && s.iter == s.n_events) stop = ST_SUCCESS;
+        if (stop == ST_RUNNING && a.rng_mode == RNG_TAPE && rng.ndraws + 8 > rng.tape_len) stop = ST_TAPE_EXHAUSTED;
+        s.status = stop;
+      }
+      stop = __shfl_sync(0xffffffffu, stop, 0);
+      if (stop == ST_RUNNING && it + 1 < a.max_events) ref_prepare_event(sm);  // (does not touch what the update reads)
+    } else {
+      // accFn2's dense part: weight / gradient-correction update (and the next event's products)
+      ref_update_rows<true, 96>(sm, gs, prod_g, (int)threadIdx.x - 32);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // The fused run kernel: dca_run.  grid = n_replicas CTAs.
 // ---------------------------------------------------------------------------
 template <int ORDER, bool TRACE>
@@ -1116,10 +1225,14 @@ __global__ void __launch_bounds__(128, 3) k_run(RunArgs a) {
   QRegs q{sm.s.n_end, sm.s.next_id, false};
   Rng rng = make_rng(a, sm.s, rep);
   float* const prod_g = sm.s.wg;  // wGradCorr itself stays in global memory (see Scratch::prod_g)
-  ref_update_rows<false>(sm, g, prod_g);  // the products of the staged state (the barrier in front of the first folds covers them)
-  for (long long it = 0; it < a.max_events; ++it) {
-    run_event<ORDER, TRACE>(sm, a, q, rng, rep, g, prod_g);
-    if (sm.s.status != ST_RUNNING) break;  // uniform after the trailing barrier
+  ref_update_rows<false, 128>(sm, g, prod_g, (int)threadIdx.x);  // the products of the staged state (the barrier in front of the first folds covers them)
+  if (TRACE) {
+    for (long long it = 0; it < a.max_events; ++it) {
+      run_event<ORDER, TRACE>(sm, a, q, rng, rep, g, prod_g);
+      if (sm.s.status != ST_RUNNING) break;  // uniform after the trailing barrier
+    }
+  } else {
+    run_events_overlapped(sm, a, q, rng, g, prod_g);
   }
   if (threadIdx.x == 0) {
     sm.s.n_end = q.n_end;
