@@ -718,6 +718,9 @@ __device__ __forceinline__ void ref_dense_update(Smem& sm) {
 // of ten AHEAD of its addition, so that the only dependence an addition waits for is the previous addition (ptxas, left
 // alone, puts every select two instructions in front of its FADD and the fold runs at 9 cycles per term instead of 4-5).
 __device__ __forceinline__ float ref_sel(const float v, const float tch, const int ch, const int f) {
+#ifdef DCA_REF_NOSEL  // timing probe only (wrong values): the fold without its selects
+  return v;
+#endif
   float u;
   asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\tselp.f32 %0, %4, %1, p;\n\t}" : "=f"(u) : "f"(v), "r"(ch), "r"(f), "f"(tch));
   return u;
