@@ -176,6 +176,37 @@ def oracle_spot_check(sims, first, n_rep, n_ev, hoff_prob):
     return True, [first + x for x in spot], None
 
 
+def ref_order_leg(device, first, n_rep=4096, warm=3000, n_ev=1000):
+    """Outside the timed region: the same workload through the REFERENCE-ORDER run kernel (dca::k_run<ORDER_REF>: the
+    Accelerate Interpreter's arithmetic, every q a dense 3479-term right fold) -- what a `RefOrder` user of dca_run gets.
+    Steady state (the 70-candidate transient of the empty grid is over after ~3000 events), device-timed; the first and
+    the last replica are compared bit for bit with the CPU oracle in the same order.  Never raises."""
+    try:
+        import numpy as np
+        import pyoracle as po
+
+        from haskelldca_b200 import Opt, Replicas
+
+        with Replicas(Opt(n_replicas=n_rep, n_events=warm + n_ev, order="ref", rng="philox", rng_seed=0, device=device,
+                          first_replica=first)) as s:
+            s.run(warm)
+            ms = s.run(n_ev)
+            u32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+            ok = True
+            for r in (0, n_rep - 1):
+                o = po.Sim(po.default_opt(order=po.ORDER_REF, rng_mode=po.RNG_PHILOX, seed=0, replica=first + r, n_events=warm + n_ev))
+                o.run(warm + n_ev)
+                want, got = o.read(), s.read_state(r)
+                ok = ok and all(np.array_equal(got[k], want[k]) for k in ("grid", "frep", "stats")) and \
+                    all(np.array_equal(u32(got[k]), u32(want[k])) for k in ("w", "wg", "avg_reward")) and got["iter"] == want["iter"]
+        return {"value": n_rep * n_ev / (ms / 1e3), "unit": UNIT, "per_gpu": True, "kernel": "dca::k_run<ORDER_REF, false>",
+                "sample": f"{n_rep} replicas x {n_ev} events after {warm} warm-up events in the same order, device-timed ({ms:.1f} ms)",
+                "oracle_check": bool(ok), "oracle_check_what": f"replicas {first} and {first + n_rep - 1} after {warm + n_ev} events: grid, frep, "
+                "stats, wNet, wGradCorr, avgReward bit-exact vs the CPU oracle in REF order"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+
+
 def inlib_allreduce_check(n_dev):
     """dca_allreduce_stats (the in-library NCCL path: one process, one handle per device, ncclCommInitAll) on the first
     min(n_dev, 4) devices of the box: its int64[10] must equal the sum of the per-device dca_sum_stats and the counters
@@ -259,6 +290,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-spot-check", action="store_true", help="skip the oracle spot check of the timed configuration")
+    ap.add_argument("--no-ref-order", action="store_true", dest="no_ref_order",
+                    help="skip the (untimed-region) throughput figure of the reference-order run kernel")
     ap.add_argument("--no-inlib-allreduce", action="store_true", dest="no_inlib_allreduce",
                     help="N > 1: skip the check of dca_allreduce_stats (in-library NCCL, one process over several devices)")
     args = ap.parse_args()
@@ -407,6 +440,8 @@ def main():
                 "rank0_mismatch": spot_msg, "events": n_ev,
                 "what": "grid, frep, stats, wNet, wGradCorr, avgReward, iter, next event bit-exact vs the CPU oracle (FAST order)"}
 
+    ref_order = ref_order_leg(local_rank, first) if (rank == 0 and not args.no_ref_order) else None
+    barrier()  # (the other ranks wait for rank 0's reference-order leg before the process group is torn down)
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         traffic, traffic_src = measured_traffic(n_rep, n_ev)
@@ -443,6 +478,7 @@ def main():
                                  "traffic (`traffic`) is one state blob in and out per replica per unit of 4096 events and frac > 1 is multi-event residency, "
                                  "not bandwidth; what binds is in `binding_ceilings` (ncu: issue slots, the shared-memory data pipe, stalls)"},
             "e2e": e2e,
+            "reference_order": ref_order,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "checks": {"all_replicas_success": bool(ok_local), "blocking_probability": bp, "events_per_step": events_all,
