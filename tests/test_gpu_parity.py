@@ -565,3 +565,52 @@ def test_async_run_and_run_many_equal_the_blocking_run():
     finally:
         for s in sets:
             s.close()
+
+
+def test_ref_order_run_kernel_without_trace():
+    """k_run<ORDER_REF, false> -- the instantiation a `RefOrder` user of dca_run (and bench.py's reference_order leg) gets:
+    all folds of an event in lock step on one warp, wGradCorr in global memory, the event-sequential tail next to the
+    dense update (run_events_overlapped).  Every other REF test runs the TRACE instantiation, which keeps the plain
+    sequence.  Chunked launches (the state crosses global memory in between), hand-offs, the 70-candidate transient of
+    the empty grid (folds on three warps), more replicas than fit the GPU at once."""
+    from haskelldca_b200 import Opt, Replicas, _ffi
+
+    n_rep, n_ev = 600, 420  # 444 CTAs of this kernel are resident on a 148-SM B200
+    kw = dict(hoff_prob=0.2, call_dur_hoff=1.0)
+    with Replicas(Opt(n_replicas=n_rep, n_events=n_ev, order="ref", rng="philox", rng_seed=11, **kw)) as sims:
+        for part in (1, 70, 149, 200):  # 420 events in four launches
+            sims.run(part)
+        s = sims.read_summary()
+        assert (s["status"] == _ffi.SUCCESS).all() and (s["iter"] == n_ev).all()
+        for r in (0, 1, 295, 443, 444, n_rep - 1):
+            o = po.Sim(po.default_opt(order=po.ORDER_REF, rng_mode=po.RNG_PHILOX, seed=11, replica=r, n_events=n_ev,
+                                      hoff_prob=0.2, call_dur_hoff=1.0))
+            o.run(n_ev)
+            assert_state_equal(sims.read_state(r), o.read())
+    # look-ahead, verify flags and the stop rules on this instantiation
+    with Replicas(Opt(n_replicas=3, n_events=900, order="ref", rng="philox", rng_seed=5, hoff_prob=0.3, hoff_lookahead=True,
+                      verify_reuse_constraint=True, verify_nelig_bounds=True)) as sims:
+        sims.run(900)
+        for r in range(3):
+            o = po.Sim(po.default_opt(order=po.ORDER_REF, rng_mode=po.RNG_PHILOX, seed=5, replica=r, n_events=900, hoff_prob=0.3,
+                                      hoff_lookahead=1))
+            o.run(900)
+            assert_state_equal(sims.read_state(r), o.read())
+    with Replicas(Opt(n_replicas=2, n_events=1000, min_loss=1e9, order="ref")) as sims:  # ZeroLoss, SimRunner.hs:161
+        sims.run(1000)
+        s = sims.read_summary()
+        assert (s["status"] == _ffi.ZERO_LOSS).all() and (s["iter"] == 51).all()
+    with Replicas(Opt(n_replicas=2, n_events=500, order="ref")) as sims:  # NaNLoss, Agent.hs:80 / SimRunner.hs:152
+        sims.run(100)
+        w = sims.read_state(1)["w"]
+        w[:] = np.nan
+        sims.write_state(1, w=w)
+        sims.run(400)
+        s = sims.read_summary()
+        assert s["status"].tolist() == [_ffi.SUCCESS, _ffi.NAN_LOSS] and s["iter"].tolist() == [500, 101]
+    with Replicas(Opt(n_events=50, order="ref", verify_reuse_constraint=True)) as sims:  # SimRunner.hs:155-156
+        g = np.zeros((7, 7, 70), np.uint8)
+        g[3, 3, 5] = g[3, 4, 5] = 1
+        sims.write_state(0, grid=g)
+        sims.run(10)
+        assert sims.read_status(0)[0] == _ffi.REUSE_VIOLATED and sims.read_status(0)[1] == 1

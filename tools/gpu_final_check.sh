@@ -6,3 +6,4 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 600 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err; tail -2 gpurun_out/r2_final_bench.err; cat gpurun_out/r2_final_bench.json
 timeout 600 python bench.py --impl reference > gpurun_out/r2_final_bench_reference_arm.json 2> gpurun_out/r2_final_ref.err; cat gpurun_out/r2_final_bench_reference_arm.json
 for n in 4096 8192; do timeout 120 python tools/prof_run.py $n 10000 20000; done
+timeout 300 python tools/ref_run.py 4096 1000 3000 ref
