@@ -119,6 +119,29 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_JSON_FD = None
+
+
+def own_stdout():
+    """The contract is ONE JSON line on stdout: libraries that print there on their own (NCCL announces its version on
+    stdout when NCCL_DEBUG is set) are sent to stderr -- file descriptor 1 is pointed at 2 and the line goes out through
+    a duplicate of the original."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def host_threads():
     """all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not cap the CPU arm)"""
     try:
@@ -273,7 +296,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -295,6 +318,7 @@ def main():
     ap.add_argument("--no-inlib-allreduce", action="store_true", dest="no_inlib_allreduce",
                     help="N > 1: skip the check of dca_allreduce_stats (in-library NCCL, one process over several devices)")
     args = ap.parse_args()
+    own_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -506,7 +530,7 @@ def main():
                                  f"materialised afterstates + dense n x 3479 dots as the reference formulates them; {threads} threads, {dt_lit:.1f} s)",
                                  "gpu_over_cpu": value / v_lit},
                 "note": "both ratios scale with the host's core count (the GPU box of one run had 16 threads, of another 32): quote them with `cores`"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     sims.close()
     if world > 1:
         dist.destroy_process_group()
