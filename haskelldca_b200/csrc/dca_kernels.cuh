@@ -506,18 +506,9 @@ __device__ __forceinline__ void apply_action(Smem& sm, int cell, bool is_end, in
 // ---------------------------------------------------------------------------
 // The dense dots of the REF order are right folds over flatten order i = cell*71 + f, i = 3478..0, of
 // float(afrep[i]) * w[i] with products and sums rounded separately (the Accelerate Interpreter).  The additions of a
-// fold are inherently sequential; the products are not: all threads form them once per event (ref_products), and a
-// fold is then 3479 dependent FADDs fed by shared-memory broadcasts.
-__device__ __forceinline__ void ref_products(Smem& sm) {
-  const RepState& s = sm.s;
-  for (int k = threadIdx.x; k < NFEAT * NCELL; k += blockDim.x) {
-    const int f = k / NCELL, cell = k - f * NCELL;
-    const int off = f * PLANE + pos_of(cell);
-    const float x = (float)s.x[off];
-    sm.t.prod_w[cell * NFEAT + f] = __fmul_rn(x, s.w[off]);
-    sm.t.prod_g[cell * NFEAT + f] = __fmul_rn(x, s.wg[off]);
-  }
-}
+// fold are inherently sequential; the products are not: they are formed once per event by all threads (ref_update_rows:
+// by the update of the previous event, or alone at launch start), and a fold is then 3479 dependent FADDs fed by
+// shared-memory broadcasts (ref_fold_lane; ref_fold_plain / ref_fold_two serve the hand-off look-ahead).
 // x . w of the current state: p0 + (p1 + (... + (p3478 + 0)))
 __device__ __noinline__ float ref_fold_plain(const float* p) {
   float acc = 0.0f;
@@ -532,40 +523,6 @@ __device__ __noinline__ float ref_fold_plain(const float* p) {
   }
   return acc;
 }
-// the same fold for the afterstate of candidate `ch` (incAfterStateFreps, Gridfuncs.hs:186-252, never materialised):
-// per cell the n_elig term (f = 70) and the channel's own term (f = ch) are re-formed when the action changes them, the
-// other 69 terms are the current state's products.  One thread; the threads of a warp stay in lock step (the inner
-// loop is the same for every channel, the re-formed term is selected by a compare).
-__device__ __noinline__ float ref_fold_candidate(const Smem& sm, const int ch, const bool is_end) {
-  const RepState& s = sm.s;
-  const unsigned long long n4 = sm.t.n4mask, n2 = sm.t.n2mask;
-  const int diff = is_end ? -1 : 1;
-  const uint8_t want = is_end ? 1 : 0;
-  float acc = 0.0f;
-#pragma unroll 1
-  for (int cell = NCELL - 1; cell >= 0; --cell) {
-    const int pos = cell + (cell * 37 >> 8);  // (cell / 7) * 8 + cell % 7 for cell < 49
-    const float* p = &sm.t.prod_w[cell * NFEAT];
-    float t70 = p[NCH];
-    if (((n2 >> cell) & 1ULL) && s.cnt2[ch * PLANE + pos] == want)  // Gridfuncs.hs:220-252
-      t70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] - diff), s.w[NCH * PLANE + pos]);
-    float tch = p[ch];
-    if ((n4 >> cell) & 1ULL)                                        // Gridfuncs.hs:212-217
-      tch = __fmul_rn((float)((int)s.x[ch * PLANE + pos] + diff), s.w[ch * PLANE + pos]);
-    acc = __fadd_rn(t70, acc);
-    static_assert(NCH % 10 == 0, "the fold loads ten products at a time");
-#pragma unroll
-    for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {  // ten loads in flight, then ten dependent additions
-      float v[10];
-#pragma unroll
-      for (int k = 0; k < 10; ++k) v[k] = p[f0 + k];
-#pragma unroll
-      for (int k = 9; k >= 0; --k) acc = __fadd_rn((f0 + k) == ch ? tch : v[k], acc);
-    }
-  }
-  return acc;
-}
-
 // Hand-off look-ahead (extension, specified at dca_config.hoff_lookahead in include/dca_b200.h): the dense right fold of the
 // state after END `ch1` at `cell` AND, if ch2 >= 0, the HOFF arrival taking `ch2` at `cell2` on that afterstate.
 // Per cell the n_elig term, the term of ch1 and the term of ch2 are re-formed when the two actions change them:
@@ -684,34 +641,11 @@ __device__ __forceinline__ void lookahead_folds(Smem& sm, const int n, const int
   }
 }
 
-// elementwise TDC update, Agent.hs:67-76, each operation rounded separately
-__device__ __forceinline__ void ref_dense_update(Smem& sm) {
-  RepState& s = sm.s;
-  Scratch& t = sm.t;
-  const float ctd = t.ctd, cavg = t.cavg, cdot = t.cdot, sg = t.sg;
-  const int act_ch = t.act_ch, diff = t.act_diff;
-  const unsigned long long n4 = t.n4mask, chg = t.chgmask;
-  for (int i = threadIdx.x; i < NFEAT * NCELL; i += blockDim.x) {
-    const int f = i / NCELL, cell = i - f * NCELL;
-    const int off = f * PLANE + pos_of(cell);
-    const int xn = s.x[off];
-    int xo = xn;
-    if (act_ch >= 0) {
-      if (f == act_ch && ((n4 >> cell) & 1ULL)) xo -= diff;
-      if (f == NCH && ((chg >> cell) & 1ULL)) xo += diff;
-    }
-    const float xnf = (float)xn, xof = (float)xo;
-    const float a1 = __fmul_rn(ctd, xof);
-    const float a3 = __fmul_rn(cdot, xnf);
-    const float g = __fsub_rn(__fadd_rn(a1, cavg), a3);
-    s.w[off] = __fsub_rn(s.w[off], g);
-    s.wg[off] = __fadd_rn(s.wg[off], __fmul_rn(sg, xof));
-  }
-}
-
 // ---- the run kernel's versions (k_run<ORDER_REF>): the same arithmetic, laid out for throughput ----
 // One lane's dense right fold in flatten order: of the products `p` of the current state when ch < 0 (V(s) on prod_w,
-// x.wGradCorr on prod_g), of the afterstate of candidate `ch` otherwise (the terms of ref_fold_candidate).  The code is the
+// x.wGradCorr on prod_g), of the afterstate of candidate `ch` otherwise (incAfterStateFreps, Gridfuncs.hs:186-252, never
+// materialised: per cell the n_elig term (f = 70) and the channel's own term (f = ch) are re-formed when the action changes
+// them, the other 69 terms are the current state's products).  The code is the
 // same for every lane, so ALL folds of an event -- up to 30 candidates, V(s) and x.wGradCorr -- run in lock step on ONE
 // warp: an event then costs the issue slots of one fold (4 instructions per step against the 4-cycle FADD chain), and the
 // fold warps of the CTAs that share an SM sit on different schedulers (the hardware rotates the warp slots of
@@ -807,7 +741,8 @@ __device__ __forceinline__ void ref_folds(Smem& sm, const int n, const bool is_e
   else if (lane == 30) t.dotg = v;
   else t.val = v;
 }
-// The elementwise TDC update (ref_dense_update's arithmetic, operation for operation) by rows of the padded layout --
+// The elementwise TDC update (Agent.hs:67-76, each operation rounded separately:
+//   g = (ctd * x + cavg) - cdot * x';  w' = w - g;  wg' = wg + sg * x)  by rows of the padded layout --
 // row (f, r) = eight bytes of frep, two 16-byte vectors of each weight array, no index arithmetic per element -- fused
 // with the products of the NEXT event (frep is in its afterstate when the update runs and nothing touches frep or the
 // weights until that event's folds).  UPDATE = false: the products alone (launch start).
@@ -1393,7 +1328,7 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   RepState& s = sm.s;
   Scratch& t = sm.t;
   const bool is_end = is_end_i != 0;
-  const int wid = warp_id(), lane = lane_id(), nthreads = blockDim.x;
+  const int wid = warp_id(), lane = lane_id();
   stage_in(sm, states + rep);
   __syncthreads();
   if (wid == 0) {
@@ -1418,15 +1353,10 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   }
   const int n = t.ncand;
   {
-    ref_products(sm);
+    // (the step kernel keeps the whole blob, wGradCorr included, in shared memory: its products go to Scratch::prod_g)
+    ref_update_rows<false, 128>(sm, &sm.s, t.prod_g, (int)threadIdx.x);
     __syncthreads();
-    for (int k = threadIdx.x; k < n; k += nthreads - 2)
-      if (threadIdx.x < nthreads - 2) t.q[k] = ref_fold_candidate(sm, t.cand[k], is_end);
-    if (threadIdx.x >= nthreads - 2) {
-      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : t.prod_g);
-      if (threadIdx.x == nthreads - 1) t.val = v;
-      else t.dotg = v;
-    }
+    ref_folds(sm, n, is_end, t.prod_g);
     __syncthreads();
   }
   if (wid == 0) {
@@ -1465,9 +1395,10 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
       }
     }
   }
+  if (threadIdx.x < 8) t.n4b_upd[threadIdx.x] = t.n4b[threadIdx.x];
   __syncthreads();
   if (mode == 1) {
-    ref_dense_update(sm);
+    ref_update_rows<true, 128>(sm, &sm.s, t.prod_g, (int)threadIdx.x);
     __syncthreads();
     stage_out(sm, states + rep);
   }
