@@ -61,7 +61,7 @@ struct RunArgs {
   unsigned n_chunks;
 };
 
-constexpr int LA_PAIRS = 1008;  // 8 rounds of 126 folding threads
+constexpr int LA_PAIRS = 504;   // 4 rounds of 126 folding threads (a candidate has at most 71 pairs)
 constexpr int LA_NONE = 255;
 // Scratch that lives next to RepState in shared memory (reference-order kernels).
 struct Scratch {
@@ -79,29 +79,39 @@ struct Scratch {
   double ev_time_prev;
   int flag;
   uint8_t cand[72];
-  // the products float(x_i) * wNet_i and float(x_i) * wGradCorr_i of the CURRENT state in flatten order i = cell * 71 + f,
-  // formed by all threads once per event: every dense right fold of the event (V(s), x.wGradCorr, one per candidate)
-  // then reads them as broadcasts and only re-forms the <= 61 terms its afterstate changes
-  float prod_w[NFEAT * NCELL + 1];
   // hand-off look-ahead (extension): the (channel to free, channel to assign in the target cell) pairs of one round
   float q_plain[72];           // V(afterstate_k): the TD target stays the real next state
   float pair_q[LA_PAIRS];
   uint8_t pair_k[LA_PAIRS];    // index into cand
   uint8_t pair_h[LA_PAIRS];    // channel in the target cell, LA_NONE = the plain afterstate of the END
   int la_npairs, la_knext;
-  // LAST: the step kernel's products with wGradCorr.  The run kernel does not allocate this array: it keeps wGradCorr
-  // itself in global memory (only the elementwise update touches it, one coalesced read and write per event, served by
-  // L2) and the products in the shared-memory bytes of RepState::wg -- 72 KB instead of 86 KB per CTA, three CTAs per SM
+  // LAST: the products float(x_i) * wNet_i and float(x_i) * wGradCorr_i of the CURRENT state in flatten order
+  // i = cell * 71 + f, formed by all threads once per event: every dense right fold of the event (V(s), x.wGradCorr, one
+  // per candidate) reads them as broadcasts and only re-forms the <= 61 terms its afterstate changes.  These two arrays
+  // are the STEP kernel's.  The run kernel does not allocate them: it keeps wNet and wGradCorr themselves in global
+  // memory (the update reads and writes them once per event, coalesced, served by L2; a fold needs two weights per cell,
+  // requested three cells ahead) and the products in the shared-memory bytes of RepState::w / RepState::wg -- 55 KB
+  // instead of 86 KB per CTA, four CTAs per SM.
+  float prod_w[NFEAT * NCELL + 1];
   float prod_g[NFEAT * NCELL + 1];
+};
+// where the reference-order kernels keep the weights and their products (see Scratch::prod_w)
+struct RefMem {
+  const float* w;   // wNet, padded plane-major layout (shared memory in the step kernel, global in the run kernel)
+  RepState* gs;     // the blob whose w / wg the update reads and writes
+  float* prod_w;    // products with wNet, flatten order (shared memory)
+  float* prod_g;    // products with wGradCorr
 };
 
 struct Smem {
   RepState s;
   Scratch t;
 };
-// shared memory of the run kernel: everything up to Scratch::prod_g
-constexpr size_t SMEM_RUN_BYTES = (offsetof(Smem, t) + offsetof(Scratch, prod_g) + 15) / 16 * 16;
-static_assert(sizeof(((RepState*)0)->wg) >= sizeof(float) * (NFEAT * NCELL + 1), "the run kernel's products live in RepState::wg");
+// shared memory of the run kernel: everything up to Scratch::prod_w
+constexpr size_t SMEM_RUN_BYTES = (offsetof(Smem, t) + offsetof(Scratch, prod_w) + 15) / 16 * 16;
+static_assert(sizeof(((RepState*)0)->wg) >= sizeof(float) * (NFEAT * NCELL + 1) && sizeof(((RepState*)0)->w) >= sizeof(float) * (NFEAT * NCELL + 1),
+              "the run kernel's products live in RepState::w / RepState::wg");
+static_assert(4 * (SMEM_RUN_BYTES + 1024) <= 232448, "four CTAs of the reference-order run kernel per SM");
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -529,7 +539,7 @@ __device__ __noinline__ float ref_fold_plain(const float* p) {
 //   in-use features: ch1 loses its user at cell (-1 on N4(cell) \ {cell}), ch2 gains one at cell2 (+1 on N4(cell2) \ {cell2});
 //   n_elig: +1 where ch1 becomes eligible (cnt2[ch1] == 1 within N2(cell) u {cell}), then -1 where ch2 was eligible on
 //   that afterstate within N2(cell2) u {cell2} (cnt2 of ch2 after the END: one less inside N2(cell) if ch2 == ch1).
-__device__ __noinline__ float ref_fold_two(const Smem& sm, const int cell1, const int ch1, const int cell2, const int ch2) {
+__device__ __noinline__ float ref_fold_two(const Smem& sm, const RefMem& m, const int cell1, const int ch1, const int cell2, const int ch2) {
   const RepState& s = sm.s;
   const unsigned long long n4a = c_tab.n4excl[cell1], n2a = c_tab.n2incl[cell1];
   const unsigned long long n4b = ch2 >= 0 ? c_tab.n4excl[cell2] : 0ULL, n2b = ch2 >= 0 ? c_tab.n2incl[cell2] : 0ULL;
@@ -538,18 +548,18 @@ __device__ __noinline__ float ref_fold_two(const Smem& sm, const int cell1, cons
 #pragma unroll 1
   for (int cell = NCELL - 1; cell >= 0; --cell) {
     const int pos = pos_of(cell);
-    const float* p = &sm.t.prod_w[cell * NFEAT];
+    const float* p = &m.prod_w[cell * NFEAT];
     const bool in2a = (n2a >> cell) & 1ULL, in2b = (n2b >> cell) & 1ULL;
     int d70 = 0;
     if (in2a && s.cnt2[ch1 * PLANE + pos] == 1) d70 += 1;
     if (in2b && (int)s.cnt2[c2 * PLANE + pos] - ((c2 == ch1 && in2a) ? 1 : 0) == 0) d70 -= 1;
     float t70 = p[NCH];
-    if (d70 != 0) t70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] + d70), s.w[NCH * PLANE + pos]);
+    if (d70 != 0) t70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] + d70), m.w[NCH * PLANE + pos]);
     const int d1 = (((n4a >> cell) & 1ULL) ? -1 : 0) + ((c2 == ch1 && ((n4b >> cell) & 1ULL)) ? 1 : 0);
     float t1 = p[ch1];
-    if (d1 != 0) t1 = __fmul_rn((float)((int)s.x[ch1 * PLANE + pos] + d1), s.w[ch1 * PLANE + pos]);
+    if (d1 != 0) t1 = __fmul_rn((float)((int)s.x[ch1 * PLANE + pos] + d1), m.w[ch1 * PLANE + pos]);
     float t2 = p[c2];
-    if (c2 != ch1 && ((n4b >> cell) & 1ULL)) t2 = __fmul_rn((float)((int)s.x[c2 * PLANE + pos] + 1), s.w[c2 * PLANE + pos]);
+    if (c2 != ch1 && ((n4b >> cell) & 1ULL)) t2 = __fmul_rn((float)((int)s.x[c2 * PLANE + pos] + 1), m.w[c2 * PLANE + pos]);
     acc = __fadd_rn(t70, acc);
 #pragma unroll
     for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {
@@ -567,7 +577,7 @@ __device__ __noinline__ float ref_fold_two(const Smem& sm, const int cell1, cons
 }
 
 // the look-ahead values of all candidates of a hand-off END: t.q[k] (selection) and t.q_plain[k] (TD target).  All threads.
-__device__ __forceinline__ void lookahead_folds(Smem& sm, const int n, const int cell1, const int cell2, const float* prod_g) {
+__device__ __forceinline__ void lookahead_folds(Smem& sm, const RefMem& m, const int n, const int cell1, const int cell2) {
   RepState& s = sm.s;
   Scratch& t = sm.t;
   const int lane = lane_id(), wid = warp_id(), nthreads = blockDim.x;
@@ -611,10 +621,10 @@ __device__ __forceinline__ void lookahead_folds(Smem& sm, const int n, const int
     if (threadIdx.x < nthreads - 2) {
       for (int p = threadIdx.x; p < np; p += nthreads - 2) {
         const int h = t.pair_h[p];
-        t.pair_q[p] = ref_fold_two(sm, cell1, t.cand[t.pair_k[p]], cell2, h == LA_NONE ? -1 : h);
+        t.pair_q[p] = ref_fold_two(sm, m, cell1, t.cand[t.pair_k[p]], cell2, h == LA_NONE ? -1 : h);
       }
     } else if (first_round) {  // V(s) and x.wGradCorr of the current state, once
-      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? t.prod_w : prod_g);
+      const float v = ref_fold_plain(threadIdx.x == nthreads - 1 ? m.prod_w : m.prod_g);
       if (threadIdx.x == nthreads - 1) t.val = v;
       else t.dotg = v;
     }
@@ -668,14 +678,24 @@ __device__ __forceinline__ void ref_add(float& acc, const float u) {
 struct RefCellTerms {  // the two terms of a cell that candidate `ch` may change
   float t70, tch;
 };
+struct RefCellW {      // the two weights they are re-formed from: of n_elig and of the channel at this cell
+  float w70, wch;
+};
+__device__ __forceinline__ RefCellW ref_cell_w(const float* w, const int cell, const int cc) {
+  const int pos = cell + (cell * 37 >> 8);  // (cell / 7) * 8 + cell % 7 for cell < 49
+  RefCellW r;
+  r.w70 = w[NCH * PLANE + pos];
+  r.wch = w[cc * PLANE + pos];
+  return r;
+}
 __device__ __forceinline__ RefCellTerms ref_cell_terms(const RepState& s, const float* pc, const int cell, const int cc,
                                                        const unsigned long long n4, const unsigned long long n2,
-                                                       const int diff, const uint8_t want) {
-  const int pos = cell + (cell * 37 >> 8);  // (cell / 7) * 8 + cell % 7 for cell < 49
+                                                       const int diff, const uint8_t want, const RefCellW ww) {
+  const int pos = cell + (cell * 37 >> 8);
   RefCellTerms r;
   // branch-free: both re-formed products are always computed, a select keeps the current state's where nothing changes
-  const float r70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] - diff), s.w[NCH * PLANE + pos]);  // Gridfuncs.hs:220-252
-  const float rch = __fmul_rn((float)((int)s.x[cc * PLANE + pos] + diff), s.w[cc * PLANE + pos]);    // Gridfuncs.hs:212-217
+  const float r70 = __fmul_rn((float)((int)s.x[NCH * PLANE + pos] - diff), ww.w70);  // Gridfuncs.hs:220-252
+  const float rch = __fmul_rn((float)((int)s.x[cc * PLANE + pos] + diff), ww.wch);   // Gridfuncs.hs:212-217
   const uint8_t c2 = s.cnt2[cc * PLANE + pos];
   const bool c70 = (((n2 >> cell) & 1ULL) != 0) & (c2 == want);
   const bool cch = (n4 >> cell) & 1ULL;
@@ -683,7 +703,8 @@ __device__ __forceinline__ RefCellTerms ref_cell_terms(const RepState& s, const 
   r.tch = cch ? rch : pc[cc];
   return r;
 }
-__device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* p, const int ch, const bool is_end) {
+// (`w`: wNet in the padded layout -- global memory in the run kernel, hence requested three cells ahead of its use)
+__device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* w, const float* p, const int ch, const bool is_end) {
   const RepState& s = sm.s;
   const bool cand = ch >= 0;
   const unsigned long long n4 = cand ? sm.t.n4mask : 0ULL, n2 = cand ? sm.t.n2mask : 0ULL;
@@ -693,7 +714,8 @@ __device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* p, cons
   static_assert(NCH % 10 == 0, "the fold handles ten terms at a time");
   float acc = 0.0f;
   const float* pc = p + (NCELL - 1) * NFEAT;
-  RefCellTerms ct = ref_cell_terms(s, pc, NCELL - 1, cc, n4, n2, diff, want);
+  RefCellW w1 = ref_cell_w(w, NCELL - 2, cc), w2 = ref_cell_w(w, NCELL - 3, cc), w3 = ref_cell_w(w, NCELL - 4, cc);
+  RefCellTerms ct = ref_cell_terms(s, pc, NCELL - 1, cc, n4, n2, diff, want, ref_cell_w(w, NCELL - 1, cc));
   float u[10];  // the selected terms of the batch that is added next
 #pragma unroll
   for (int k = 0; k < 10; ++k) u[k] = ref_sel(pc[NCH - 10 + k], ct.tch, ch, NCH - 10 + k);
@@ -702,7 +724,10 @@ __device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* p, cons
     // the next cell's two terms (cell 0: its own again, unused), in flight while this cell's 71 terms are added
     const int celln = cell > 0 ? cell - 1 : 0;
     const float* pn = p + celln * NFEAT;
-    const RefCellTerms cn = ref_cell_terms(s, pn, celln, cc, n4, n2, diff, want);
+    const RefCellTerms cn = ref_cell_terms(s, pn, celln, cc, n4, n2, diff, want, w1);
+    w1 = w2;
+    w2 = w3;
+    w3 = ref_cell_w(w, cell > 3 ? cell - 4 : 0, cc);  // (the next cell of iteration cell - 3: requested three iterations ahead)
     ref_add(acc, ct.t70);
 #pragma unroll
     for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {
@@ -728,15 +753,15 @@ __device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* p, cons
 }
 // the folds of one event without look-ahead: warp 0 = candidates 0..29 (lanes 0..29), x.wGradCorr (lane 30), V(s) (lane 31);
 // warps 1.. = candidates 30.. (only the transient of the empty grid has that many)
-__device__ __forceinline__ void ref_folds(Smem& sm, const int n, const bool is_end, const float* prod_g) {
+__device__ __forceinline__ void ref_folds(Smem& sm, const RefMem& m, const int n, const bool is_end) {
   Scratch& t = sm.t;
   const int wid = warp_id(), lane = lane_id();
   const int k = wid == 0 ? (lane < 30 ? lane : -1) : 30 + 32 * (wid - 1) + lane;
   const bool plain = wid == 0 && lane >= 30;
   const bool is_cand = k >= 0 && k < n;
   if (!(plain || is_cand)) return;
-  const float* p = (plain && lane == 30) ? prod_g : t.prod_w;
-  const float v = ref_fold_lane(sm, p, is_cand ? (int)t.cand[k] : -1, is_end);
+  const float* p = (plain && lane == 30) ? m.prod_g : m.prod_w;
+  const float v = ref_fold_lane(sm, m.w, p, is_cand ? (int)t.cand[k] : -1, is_end);
   if (is_cand) t.q[k] = v;
   else if (lane == 30) t.dotg = v;
   else t.val = v;
@@ -747,22 +772,28 @@ __device__ __forceinline__ void ref_folds(Smem& sm, const int n, const bool is_e
 // with the products of the NEXT event (frep is in its afterstate when the update runs and nothing touches frep or the
 // weights until that event's folds).  UPDATE = false: the products alone (launch start).
 template <bool UPDATE, int NT>
-__device__ __forceinline__ void ref_update_rows(Smem& sm, RepState* gs, float* prod_g, const int tid) {
+__device__ __forceinline__ void ref_update_rows(Smem& sm, const RefMem& m, const int tid) {
   RepState& s = sm.s;
   Scratch& t = sm.t;
+  RepState* const gs = m.gs;
   const float ctd = t.ctd, cavg = t.cavg, cdot = t.cdot, sg = t.sg;
   const int act_ch = UPDATE ? t.act_ch : -1, diff = t.act_diff;
   constexpr int NIT = (NROW + NT - 1) / NT;   // rows per thread
-  constexpr int CH = NT >= 128 ? 4 : 3;       // rows whose wGradCorr is requested together
+#ifndef DCA_REF_UPD_CH
+#define DCA_REF_UPD_CH 2
+#endif
+  constexpr int CH = DCA_REF_UPD_CH;          // rows whose weights are requested together
 #pragma unroll
   for (int it0 = 0; it0 < NIT; it0 += CH) {
-    // wGradCorr lives in global memory: the rows of a chunk are requested before the first one is used
-    float4 ga[CH], gb[CH];
+    // the weights may live in global memory: the rows of a chunk are requested before the first one is used
+    float4 wa[CH], wb[CH], ga[CH], gb[CH];
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       const int row = tid + NT * (it0 + j);
       if (it0 + j < NIT && row < NROW) {
         const int f = row / ROWS, off = f * PLANE + (row - f * ROWS) * ROWPAD;
+        wa[j] = *reinterpret_cast<const float4*>(&gs->w[off]);
+        wb[j] = *reinterpret_cast<const float4*>(&gs->w[off + 4]);
         ga[j] = *reinterpret_cast<const float4*>(&gs->wg[off]);
         gb[j] = *reinterpret_cast<const float4*>(&gs->wg[off + 4]);
       }
@@ -777,16 +808,15 @@ __device__ __forceinline__ void ref_update_rows(Smem& sm, RepState* gs, float* p
       uint2 xo = xn;
       if (UPDATE && act_ch >= 0) {
         if (f == act_ch) {  // x_old = x_new - diff on N4 \ {cell}
-          const uint2 m = t.n4b_upd[r];
-          if (diff > 0) { xo.x -= m.x; xo.y -= m.y; } else { xo.x += m.x; xo.y += m.y; }
+          const uint2 mk = t.n4b_upd[r];
+          if (diff > 0) { xo.x -= mk.x; xo.y -= mk.y; } else { xo.x += mk.x; xo.y += mk.y; }
         }
         if (f == NCH) {     // n_elig: x_old = x_new + diff on the changed cells
-          const uint2 m = t.chgb[r];
-          if (diff > 0) { xo.x += m.x; xo.y += m.y; } else { xo.x -= m.x; xo.y -= m.y; }
+          const uint2 mk = t.chgb[r];
+          if (diff > 0) { xo.x += mk.x; xo.y += mk.y; } else { xo.x -= mk.x; xo.y -= mk.y; }
         }
       }
-      float4 wa = *reinterpret_cast<const float4*>(&s.w[off]), wb = *reinterpret_cast<const float4*>(&s.w[off + 4]);
-      float w[7] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z};
+      float w[7] = {wa[j].x, wa[j].y, wa[j].z, wa[j].w, wb[j].x, wb[j].y, wb[j].z};
       float g[7] = {ga[j].x, ga[j].y, ga[j].z, ga[j].w, gb[j].x, gb[j].y, gb[j].z};
 #pragma unroll
       for (int c = 0; c < COLS; ++c) {
@@ -800,12 +830,12 @@ __device__ __forceinline__ void ref_update_rows(Smem& sm, RepState* gs, float* p
           g[c] = __fadd_rn(g[c], __fmul_rn(sg, xof));
         }
         const int i = (r * COLS + c) * NFEAT + f;  // flatten order
-        t.prod_w[i] = __fmul_rn(xnf, w[c]);
-        prod_g[i] = __fmul_rn(xnf, g[c]);
+        m.prod_w[i] = __fmul_rn(xnf, w[c]);
+        m.prod_g[i] = __fmul_rn(xnf, g[c]);
       }
       if (UPDATE) {  // (the pad column goes back as it came)
-        *reinterpret_cast<float4*>(&s.w[off]) = make_float4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<float4*>(&s.w[off + 4]) = make_float4(w[4], w[5], w[6], wb.w);
+        *reinterpret_cast<float4*>(&gs->w[off]) = make_float4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<float4*>(&gs->w[off + 4]) = make_float4(w[4], w[5], w[6], wb[j].w);
         *reinterpret_cast<float4*>(&gs->wg[off]) = make_float4(g[0], g[1], g[2], g[3]);
         *reinterpret_cast<float4*>(&gs->wg[off + 4]) = make_float4(g[4], g[5], g[6], gb[j].w);
       }
@@ -880,20 +910,20 @@ __device__ __forceinline__ void stage_out(const Smem& sm, RepState* g) {
   for (int i = threadIdx.x; i < (int)(sizeof(RepState) / 16); i += blockDim.x) dst[i] = src[i];
 }
 
-// the run kernel's staging: everything but wGradCorr, which stays in global memory (its shared-memory bytes hold products)
-static_assert(offsetof(RepState, wg) % 16 == 0 && offsetof(RepState, x) % 16 == 0, "RepState::wg is a 16-byte aligned range");
+// the run kernel's staging: everything but wNet and wGradCorr, which stay in global memory (their shared-memory bytes hold
+// the products)
+static_assert(offsetof(RepState, w) == 0 && offsetof(RepState, wg) == sizeof(((RepState*)0)->w) && offsetof(RepState, x) % 16 == 0,
+              "RepState starts with w and wg, a 16-byte aligned range");
 __device__ __forceinline__ void stage_in_run(Smem& sm, const RepState* g) {
   const uint4* src = reinterpret_cast<const uint4*>(g);
   uint4* dst = reinterpret_cast<uint4*>(&sm.s);
-  constexpr int A = (int)(offsetof(RepState, wg) / 16), B = (int)(offsetof(RepState, x) / 16), N = (int)(sizeof(RepState) / 16);
-  for (int i = threadIdx.x; i < A; i += blockDim.x) dst[i] = src[i];
+  constexpr int B = (int)(offsetof(RepState, x) / 16), N = (int)(sizeof(RepState) / 16);
   for (int i = B + threadIdx.x; i < N; i += blockDim.x) dst[i] = src[i];
 }
 __device__ __forceinline__ void stage_out_run(const Smem& sm, RepState* g) {
   const uint4* src = reinterpret_cast<const uint4*>(&sm.s);
   uint4* dst = reinterpret_cast<uint4*>(g);
-  constexpr int A = (int)(offsetof(RepState, wg) / 16), B = (int)(offsetof(RepState, x) / 16), N = (int)(sizeof(RepState) / 16);
-  for (int i = threadIdx.x; i < A; i += blockDim.x) dst[i] = src[i];
+  constexpr int B = (int)(offsetof(RepState, x) / 16), N = (int)(sizeof(RepState) / 16);
   for (int i = B + threadIdx.x; i < N; i += blockDim.x) dst[i] = src[i];
 }
 
@@ -922,7 +952,7 @@ __device__ __forceinline__ Rng make_rng(const RunArgs& a, const RepState& s, int
 // ---------------------------------------------------------------------------
 template <int ORDER, bool TRACE>
 __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, Rng& rng,
-                                          int rep, RepState* gs, float* prod_g) {
+                                          int rep, const RefMem& m) {
   DCA_RCLK_START
   RepState& s = sm.s;
   Scratch& t = sm.t;
@@ -954,9 +984,9 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
     // (the products of the current state are in place: formed at launch start and by every update since)
     const bool la = a.lookahead && is_end && n > 0 && s.ev_hoff != HOFF_NONE;  // uniform: the departure half of a hand-off
     if (la) {
-      lookahead_folds(sm, n, t.ev_cell, s.ev_hoff, prod_g);
+      lookahead_folds(sm, m, n, t.ev_cell, s.ev_hoff);
     } else {
-      ref_folds(sm, n, is_end, prod_g);
+      ref_folds(sm, m, n, is_end);
       for (int k = threadIdx.x; k < n; k += nthreads) t.q_plain[k] = 0.0f;  // (unused without look-ahead)
     }
     if (threadIdx.x == 0) t.flag = la ? 1 : 0;
@@ -1008,7 +1038,7 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
   __syncthreads();
   DCA_RCLK(2)
   // ---- accFn2's dense part: weight / gradient-correction update (and the next event's products) ----
-  ref_update_rows<true, 128>(sm, gs, prod_g, (int)threadIdx.x);
+  ref_update_rows<true, 128>(sm, m, (int)threadIdx.x);
   if (TRACE) state_hashes(sm);
   __syncthreads();
   DCA_RCLK(3)
@@ -1067,8 +1097,7 @@ __device__ __forceinline__ void ref_prepare_event(Smem& sm) {  // warp 0: candid
   }
   __syncwarp();
 }
-__device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a, QRegs& q, Rng& rng, RepState* gs,
-                                                      float* prod_g) {
+__device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a, QRegs& q, Rng& rng, const RefMem& m) {
   RepState& s = sm.s;
   Scratch& t = sm.t;
   const int wid = warp_id(), lane = lane_id();
@@ -1081,8 +1110,8 @@ __device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a
     const int n = t.ncand;
     const bool is_end = t.ev_is_end;
     const bool la = a.lookahead && is_end && n > 0 && s.ev_hoff != HOFF_NONE;  // uniform: the departure half of a hand-off
-    if (la) lookahead_folds(sm, n, t.ev_cell, s.ev_hoff, prod_g);
-    else ref_folds(sm, n, is_end, prod_g);
+    if (la) lookahead_folds(sm, m, n, t.ev_cell, s.ev_hoff);
+    else ref_folds(sm, m, n, is_end);
     __syncthreads();
     DCA_RCLK(1)
     int act = -1;
@@ -1145,7 +1174,7 @@ __device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a
       if (stop == ST_RUNNING && it + 1 < a.max_events) ref_prepare_event(sm);  // (does not touch what the update reads)
     } else {
       // accFn2's dense part: weight / gradient-correction update (and the next event's products)
-      ref_update_rows<true, 96>(sm, gs, prod_g, (int)threadIdx.x - 32);
+      ref_update_rows<true, 96>(sm, m, (int)threadIdx.x - 32);
     }
   }
 }
@@ -1154,7 +1183,7 @@ __device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a
 // The fused run kernel: dca_run.  grid = n_replicas CTAs.
 // ---------------------------------------------------------------------------
 template <int ORDER, bool TRACE>
-__global__ void __launch_bounds__(128, 3) k_run(RunArgs a) {
+__global__ void __launch_bounds__(128, 4) k_run(RunArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int rep = blockIdx.x;
@@ -1165,15 +1194,16 @@ __global__ void __launch_bounds__(128, 3) k_run(RunArgs a) {
   if (!sm.s.initialized || sm.s.status != ST_RUNNING) return;  // uniform
   QRegs q{sm.s.n_end, sm.s.next_id, false};
   Rng rng = make_rng(a, sm.s, rep);
-  float* const prod_g = sm.s.wg;  // wGradCorr itself stays in global memory (see Scratch::prod_g)
-  ref_update_rows<false, 128>(sm, g, prod_g, (int)threadIdx.x);  // the products of the staged state (the barrier in front of the first folds covers them)
+  // wNet and wGradCorr themselves stay in global memory; their shared-memory bytes hold the products (see Scratch::prod_w)
+  const RefMem m{g->w, g, sm.s.w, sm.s.wg};
+  ref_update_rows<false, 128>(sm, m, (int)threadIdx.x);  // the products of the staged state (the barrier in front of the first folds covers them)
   if (TRACE) {
     for (long long it = 0; it < a.max_events; ++it) {
-      run_event<ORDER, TRACE>(sm, a, q, rng, rep, g, prod_g);
+      run_event<ORDER, TRACE>(sm, a, q, rng, rep, m);
       if (sm.s.status != ST_RUNNING) break;  // uniform after the trailing barrier
     }
   } else {
-    run_events_overlapped(sm, a, q, rng, g, prod_g);
+    run_events_overlapped(sm, a, q, rng, m);
   }
   if (threadIdx.x == 0) {
     sm.s.n_end = q.n_end;
@@ -1329,6 +1359,7 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   Scratch& t = sm.t;
   const bool is_end = is_end_i != 0;
   const int wid = warp_id(), lane = lane_id();
+  const RefMem m{sm.s.w, &sm.s, t.prod_w, t.prod_g};  // (the step kernel keeps the whole blob and its own product arrays in shared memory)
   stage_in(sm, states + rep);
   __syncthreads();
   if (wid == 0) {
@@ -1353,10 +1384,9 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   }
   const int n = t.ncand;
   {
-    // (the step kernel keeps the whole blob, wGradCorr included, in shared memory: its products go to Scratch::prod_g)
-    ref_update_rows<false, 128>(sm, &sm.s, t.prod_g, (int)threadIdx.x);
+    ref_update_rows<false, 128>(sm, m, (int)threadIdx.x);
     __syncthreads();
-    ref_folds(sm, n, is_end, t.prod_g);
+    ref_folds(sm, m, n, is_end);
     __syncthreads();
   }
   if (wid == 0) {
@@ -1398,7 +1428,7 @@ __global__ void __launch_bounds__(128) k_step(RepState* states, int rep, int mod
   if (threadIdx.x < 8) t.n4b_upd[threadIdx.x] = t.n4b[threadIdx.x];
   __syncthreads();
   if (mode == 1) {
-    ref_update_rows<true, 128>(sm, &sm.s, t.prod_g, (int)threadIdx.x);
+    ref_update_rows<true, 128>(sm, m, (int)threadIdx.x);
     __syncthreads();
     stage_out(sm, states + rep);
   }
