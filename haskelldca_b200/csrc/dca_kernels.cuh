@@ -54,7 +54,7 @@ struct RunArgs {
   const unsigned long long* tape_off;  // [n_replicas + 1]
   TraceRec* trace;                  // [n_replicas][trace_cap] or null
   int trace_cap;
-  int lookahead;                    // hand-off look-ahead (extension; REF-order kernel only)
+  int lookahead;                    // hand-off look-ahead (extension; both orders: lookahead_folds here, k_run_fast<true, true>)
   // FAST kernel: the launch is cut into units (replica, chunk of chunk_events events), one CTA each -- see k_run_fast
   unsigned* chunk_done;             // [n_replicas]: chunks of the replica completed in this launch (zeroed before the launch)
   long long chunk_events;
