@@ -61,6 +61,7 @@ struct RunArgs {
   unsigned n_chunks;
 };
 
+constexpr int PROW = 72;        // floats per cell in the product arrays: 71 features + 1 pad, so that a row starts on 16 bytes
 constexpr int LA_PAIRS = 504;   // 4 rounds of 126 folding threads (a candidate has at most 71 pairs)
 constexpr int LA_NONE = 255;
 // Scratch that lives next to RepState in shared memory (reference-order kernels).
@@ -92,8 +93,8 @@ struct Scratch {
   // memory (the update reads and writes them once per event, coalesced, served by L2; a fold needs two weights per cell,
   // requested three cells ahead) and the products in the shared-memory bytes of RepState::w / RepState::wg -- 55 KB
   // instead of 86 KB per CTA, four CTAs per SM.
-  float prod_w[NFEAT * NCELL + 1];
-  float prod_g[NFEAT * NCELL + 1];
+  alignas(16) float prod_w[PROW * NCELL];
+  alignas(16) float prod_g[PROW * NCELL];
 };
 // where the reference-order kernels keep the weights and their products (see Scratch::prod_w)
 struct RefMem {
@@ -109,7 +110,7 @@ struct Smem {
 };
 // shared memory of the run kernel: everything up to Scratch::prod_w
 constexpr size_t SMEM_RUN_BYTES = (offsetof(Smem, t) + offsetof(Scratch, prod_w) + 15) / 16 * 16;
-static_assert(sizeof(((RepState*)0)->wg) >= sizeof(float) * (NFEAT * NCELL + 1) && sizeof(((RepState*)0)->w) >= sizeof(float) * (NFEAT * NCELL + 1),
+static_assert(sizeof(((RepState*)0)->wg) >= sizeof(float) * PROW * NCELL && sizeof(((RepState*)0)->w) >= sizeof(float) * PROW * NCELL,
               "the run kernel's products live in RepState::w / RepState::wg");
 static_assert(4 * (SMEM_RUN_BYTES + 1024) <= 232448, "four CTAs of the reference-order run kernel per SM");
 
@@ -514,7 +515,7 @@ __device__ __forceinline__ void apply_action(Smem& sm, int cell, bool is_end, in
 // ---------------------------------------------------------------------------
 // REF order: reference-literal arithmetic (Accelerate Interpreter)
 // ---------------------------------------------------------------------------
-// The dense dots of the REF order are right folds over flatten order i = cell*71 + f, i = 3478..0, of
+// The dense dots of the REF order are right folds over flatten order i = cell*71 + f, i = 3478..0 (stored in rows of PROW floats), of
 // float(afrep[i]) * w[i] with products and sums rounded separately (the Accelerate Interpreter).  The additions of a
 // fold are inherently sequential; the products are not: they are formed once per event by all threads (ref_update_rows:
 // by the update of the previous event, or alone at launch start), and a fold is then 3479 dependent FADDs fed by
@@ -522,14 +523,18 @@ __device__ __forceinline__ void apply_action(Smem& sm, int cell, bool is_end, in
 // x . w of the current state: p0 + (p1 + (... + (p3478 + 0)))
 __device__ __noinline__ float ref_fold_plain(const float* p) {
   float acc = 0.0f;
-  static_assert((NFEAT * NCELL) % 7 == 0, "the fold loads seven products at a time");
-#pragma unroll 2
-  for (int i0 = NFEAT * NCELL - 7; i0 >= 0; i0 -= 7) {
-    float v[7];
+#pragma unroll 1
+  for (int cell = NCELL - 1; cell >= 0; --cell) {
+    const float* pc = p + cell * PROW;
+    acc = __fadd_rn(pc[NCH], acc);
 #pragma unroll
-    for (int k = 0; k < 7; ++k) v[k] = p[i0 + k];
+    for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {
+      float v[10];
 #pragma unroll
-    for (int k = 6; k >= 0; --k) acc = __fadd_rn(v[k], acc);
+      for (int k = 0; k < 10; ++k) v[k] = pc[f0 + k];
+#pragma unroll
+      for (int k = 9; k >= 0; --k) acc = __fadd_rn(v[k], acc);
+    }
   }
   return acc;
 }
@@ -548,7 +553,7 @@ __device__ __noinline__ float ref_fold_two(const Smem& sm, const RefMem& m, cons
 #pragma unroll 1
   for (int cell = NCELL - 1; cell >= 0; --cell) {
     const int pos = pos_of(cell);
-    const float* p = &m.prod_w[cell * NFEAT];
+    const float* p = &m.prod_w[cell * PROW];
     const bool in2a = (n2a >> cell) & 1ULL, in2b = (n2b >> cell) & 1ULL;
     int d70 = 0;
     if (in2a && s.cnt2[ch1 * PLANE + pos] == 1) d70 += 1;
@@ -711,40 +716,54 @@ __device__ __noinline__ float ref_fold_lane(const Smem& sm, const float* w, cons
   const int cc = cand ? ch : 0;
   const int diff = is_end ? -1 : 1;
   const uint8_t want = is_end ? 1 : 0;
-  static_assert(NCH % 10 == 0, "the fold handles ten terms at a time");
+  // A cell's row of PROW = 72 floats is read as six batches of twelve (three 16-byte loads each): features 60-71 (70 is
+  // the n_elig term, handled apart; 71 the pad), 48-59, ..., 0-11.  u holds the selected terms of the batch added next.
+  static_assert(PROW == 72 && NCH == 70, "six batches of twelve");
   float acc = 0.0f;
-  const float* pc = p + (NCELL - 1) * NFEAT;
+  const float* pc = p + (NCELL - 1) * PROW;
   RefCellW w1 = ref_cell_w(w, NCELL - 2, cc), w2 = ref_cell_w(w, NCELL - 3, cc), w3 = ref_cell_w(w, NCELL - 4, cc);
   RefCellTerms ct = ref_cell_terms(s, pc, NCELL - 1, cc, n4, n2, diff, want, ref_cell_w(w, NCELL - 1, cc));
-  float u[10];  // the selected terms of the batch that is added next
+  float u[12];
+  {
+    float v[12];
 #pragma unroll
-  for (int k = 0; k < 10; ++k) u[k] = ref_sel(pc[NCH - 10 + k], ct.tch, ch, NCH - 10 + k);
+    for (int j = 0; j < 3; ++j) {
+      const float4 q4 = *reinterpret_cast<const float4*>(pc + 60 + 4 * j);
+      v[4 * j] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) u[k] = ref_sel(v[k], ct.tch, ch, 60 + k);
+  }
 #pragma unroll 1
   for (int cell = NCELL - 1; cell >= 0; --cell) {
     // the next cell's two terms (cell 0: its own again, unused), in flight while this cell's 71 terms are added
     const int celln = cell > 0 ? cell - 1 : 0;
-    const float* pn = p + celln * NFEAT;
+    const float* pn = p + celln * PROW;
     const RefCellTerms cn = ref_cell_terms(s, pn, celln, cc, n4, n2, diff, want, w1);
     w1 = w2;
     w2 = w3;
     w3 = ref_cell_w(w, cell > 3 ? cell - 4 : 0, cc);  // (the next cell of iteration cell - 3: requested three iterations ahead)
     ref_add(acc, ct.t70);
 #pragma unroll
-    for (int f0 = NCH - 10; f0 >= 0; f0 -= 10) {
-      // the batch below (the top batch of the next cell after the last one), selected while this one is added
-      const float* q = f0 > 0 ? pc + (f0 - 10) : pn + (NCH - 10);
-      const int fq = f0 > 0 ? f0 - 10 : NCH - 10;
-      const float tq = f0 > 0 ? ct.tch : cn.tch;
-      float v[10], un[10];
+    for (int b = 5; b >= 0; --b) {
+      // batch b of this cell is added (b == 5: its ten terms 69..60) while the batch below -- the top batch of the next
+      // cell after the last one -- is loaded and selected
+      const float* q = b > 0 ? pc + 12 * (b - 1) : pn + 60;
+      const int fq = b > 0 ? 12 * (b - 1) : 60;
+      const float tq = b > 0 ? ct.tch : cn.tch;
+      float v[12], un[12];
 #pragma unroll
-      for (int k = 0; k < 10; ++k) v[k] = q[k];
-#pragma unroll
-      for (int k = 9; k >= 0; --k) {
-        ref_add(acc, u[k]);
-        un[k] = ref_sel(v[k], tq, ch, fq + k);
+      for (int j = 0; j < 3; ++j) {
+        const float4 q4 = *reinterpret_cast<const float4*>(q + 4 * j);
+        v[4 * j] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
       }
 #pragma unroll
-      for (int k = 0; k < 10; ++k) u[k] = un[k];
+      for (int k = 11; k >= 0; --k) {
+        if (b < 5 || k < 10) ref_add(acc, u[k]);
+        if (b > 0 || k < 10) un[k] = ref_sel(v[k], tq, ch, fq + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 12; ++k) u[k] = un[k];
     }
     ct = cn;
     pc = pn;
@@ -829,7 +848,7 @@ __device__ __forceinline__ void ref_update_rows(Smem& sm, const RefMem& m, const
           w[c] = __fsub_rn(w[c], gr);
           g[c] = __fadd_rn(g[c], __fmul_rn(sg, xof));
         }
-        const int i = (r * COLS + c) * NFEAT + f;  // flatten order
+        const int i = (r * COLS + c) * PROW + f;  // flatten order, rows of PROW floats
         m.prod_w[i] = __fmul_rn(xnf, w[c]);
         m.prod_g[i] = __fmul_rn(xnf, g[c]);
       }
