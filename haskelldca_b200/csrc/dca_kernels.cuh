@@ -662,13 +662,14 @@ __device__ __forceinline__ void lookahead_folds(Smem& sm, const RefMem& m, const
 // materialised: per cell the n_elig term (f = 70) and the channel's own term (f = ch) are re-formed when the action changes
 // them, the other 69 terms are the current state's products).  The code is the
 // same for every lane, so ALL folds of an event -- up to 30 candidates, V(s) and x.wGradCorr -- run in lock step on ONE
-// warp: an event then costs the issue slots of one fold (4 instructions per step against the 4-cycle FADD chain), and the
-// fold warps of the CTAs that share an SM sit on different schedulers (the hardware rotates the warp slots of
-// co-resident CTAs over the sub-partitions, tools/microbench/placement.cu).  Before: candidates on warp 0, the two plain
-// folds on warp 3, two CTAs per SM -> two fold warps per scheduler, 6.5 issue cycles per step.
-// The schedule is explicit (volatile asm keeps the order): a term is selected -- `f == ch ? re-formed : product` -- one batch
-// of ten AHEAD of its addition, so that the only dependence an addition waits for is the previous addition (ptxas, left
-// alone, puts every select two instructions in front of its FADD and the fold runs at 9 cycles per term instead of 4-5).
+// warp: an event then costs the issue slots of one fold (compare, select, FADD and a quarter of a 16-byte load per term
+// against the dependent FADD chain, measured at ~4.6 cycles per term), and the fold warps of the CTAs that share an SM sit
+// on different schedulers (the hardware rotates the warp slots of co-resident CTAs over the sub-partitions,
+// tools/microbench/placement.cu).  Before: candidates on warp 0, the two plain folds on warp 3, two CTAs per SM -> two
+// fold warps per scheduler, 6.5 issue cycles per term.
+// A term is selected -- `f == ch ? re-formed : product` -- one batch AHEAD of its addition, so that the only dependence an
+// addition waits for is the previous addition (written the plain way, every select lands two instructions in front of its
+// FADD and the fold runs at 9 cycles per term instead of 5-6; profiles/r2_ref_order_kernel.md).
 __device__ __forceinline__ float ref_sel(const float v, const float tch, const int ch, const int f) {
 #ifdef DCA_REF_NOSEL  // timing probe only (wrong values): the fold without its selects
   return v;
