@@ -156,3 +156,28 @@ def test_dca_create_rejects_a_run_longer_than_the_32_bit_event_ids_allow():
     h = C.c_void_p()
     assert L.dca_create(C.byref(cfg), C.byref(h)) == -1 and not h.value
     assert b"n_events" in L.dca_last_error(None)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs first): exactly one line on stdout, a JSON object with the
+    contract's keys; whatever else a library writes to file descriptor 1 goes to stderr (bench.own_stdout)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-events", "200"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["unit"] == "events/s" and rec["higher_is_better"] is True
+    assert rec["value"] > 0 and rec["cpu_baseline"]["kind"] == "port" and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["d2h_bytes_per_step"] == 0 and rec["gpu_launches"] == 0
+    # the redirection itself: a write to fd 1 after own_stdout() must not reach stdout
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.own_stdout(); os.write(1, b'library banner\\n'); "
+            "bench.emit({'ok': 1})" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip() == '{"ok": 1}' and "library banner" in out.stderr
