@@ -71,6 +71,12 @@ struct Scratch {
   uint2 n2b[8];    // row byte masks: N2(cell) u {cell}
   uint2 chgb[8];   // row byte masks: cells whose n_elig changes (chosen action)
   uint2 n4b_upd[8];  // n4b of the event whose update is running (the run kernel builds the next event's masks meanwhile)
+  // run kernel, environmentStep ahead of the decision (env_ahead / env_post): the current event as env_ahead found it, the
+  // END event it pushed without a channel, and what warp 3 -- the owner of the queue counters and the random source --
+  // publishes for warp 0's stop rules
+  int cur_type, cur_ch, cur_hoff, pend_slot, q_overflow;
+  unsigned q_n_end;
+  unsigned long long rng_ndraws;
   unsigned long long n4mask, n2mask, chgmask;
   unsigned long long hash_grid, hash_frep;
   float ctd, cavg, cdot, sg;   // TDC scalars of this event
@@ -283,7 +289,9 @@ __device__ __forceinline__ void q_reassign(RepState& s, const QRegs& q, int cell
     if (s.q_key[i] == want) s.q_key[i] = (uint16_t)((cell << 7) | to);
 }
 // pop (EventGen.hs:39-50): argmin over (time, id); writes the event into s.ev_*
-__device__ __forceinline__ void q_pop(RepState& s, QRegs& q) {
+// (`pend`: slot of an END event whose key still lacks its channel -- env_ahead -- or null: follows the entry when the
+//  pop moves it, -1 when it is the event popped)
+__device__ __forceinline__ void q_pop(RepState& s, QRegs& q, int* pend = nullptr) {
   const unsigned total = QNEW + q.n_end;
   const int lane = lane_id();
   unsigned long long bt = 0xFFFFFFFFFFFFFFFFULL;
@@ -316,6 +324,10 @@ __device__ __forceinline__ void q_pop(RepState& s, QRegs& q) {
     }
   } else {
     unsigned last = QNEW + q.n_end - 1;
+    if (pend) {
+      if ((int)slot == *pend) *pend = -1;
+      else if ((int)last == *pend) *pend = (int)slot;
+    }
     if (lane == 0) {
       unsigned key = s.q_key[slot];
       s.ev_time = s.q_time[slot];
@@ -1099,10 +1111,11 @@ __device__ __forceinline__ void run_event(Smem& sm, const RunArgs& a, QRegs& q, 
 
 // ---------------------------------------------------------------------------
 // The event loop of the run kernel without the parity trace: the same steps as run_event, arranged so that the
-// event-sequential tail of an event runs NEXT TO its dense update instead of in front of it.  Once the decision and
-// the TD scalars are published, warps 1-3 run the update (and form the next event's products) while warp 0 runs
-// environmentStep, the stop rules and the next event's candidate list -- none of which reads the weights.  Three CTA
-// barriers per event instead of five.
+// event-sequential work of an event runs NEXT TO its folds and its dense update instead of between them.  While the
+// folds run, warp 3 does the part of environmentStep that does not depend on WHICH channel is chosen (env_ahead); once
+// the decision and the TD scalars are published, warps 1-3 run the update (and form the next event's products) while
+// warp 0 finishes environmentStep (env_post), applies the stop rules and builds the next event's candidate list -- none
+// of which reads the weights.  Three CTA barriers per event instead of five.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void ref_prepare_event(Smem& sm) {  // warp 0: candidates and masks of the current event
   RepState& s = sm.s;
@@ -1114,6 +1127,104 @@ __device__ __forceinline__ void ref_prepare_event(Smem& sm) {  // warp 0: candid
     t.ncand = n;
     t.ev_cell = cell;
     t.ev_is_end = is_end;
+    t.cur_type = s.ev_type;
+    t.cur_ch = s.ev_ch;
+    t.cur_hoff = s.ev_hoff;
+  }
+  __syncwarp();
+}
+// environmentStep (Simulator.hs:101-134) in two parts, as in the FAST kernel: what an event does to the queue depends on
+// WHETHER a channel is chosen (`accepted` = it has a candidate), not on which.  env_ahead -- warp 3, while the folds of
+// the event run -- books the statistics, draws the random numbers, pushes the new events (an END event without its
+// channel: key channel CH_NONE_YET) and pops the next event into s.ev_*; env_post -- warp 0, after the decision -- writes
+// the chosen channel into that END event (or into s.ev_ch when it is the event just popped) and performs the
+// reassignment of an END (Simulator.hs:129-130) on the queue as the pop left it.  Pop order depends on (time, id) only,
+// so the result is the one of environment_step.
+constexpr int CH_NONE_YET = 127;
+__device__ __forceinline__ void env_ahead(Smem& sm, QRegs& q, Rng& rng, const bool accepted) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const int lane = lane_id();
+  const int type = t.cur_type, cell = t.ev_cell, ev_hoff = t.cur_hoff;
+  const double time = s.ev_time;
+  int pend = -1;
+  if (lane == 0) {  // Stats hooks, Stats.hs:61-81 as called from Simulator.hs:105-114
+    if (type == EV_NEW) {
+      s.stats[6]++; s.stats[0]++;
+      if (accepted) s.stats[1]++;
+      else { s.stats[2]++; s.stats[7]++; }
+    } else if (type == EV_HOFF) {
+      s.stats[3]++;
+      if (!accepted) { s.stats[2]++; s.stats[7]++; }  // Simulator.hs:113
+    } else {
+      s.stats[4]++;
+    }
+  }
+  if (type == EV_NEW) {
+    const double dt = rng.exponential(s.mean_new);  // generateNewEvent, EventGen.hs:75-85
+    q_push_new(s, q, cell, __dadd_rn(time, dt));
+    if (accepted) {
+      const double p = rng.uniform();  // Simulator.hs:121, drawn even when hoffProb == 0
+      pend = QNEW + q.n_end < (unsigned)QCAP ? (int)(QNEW + q.n_end) : -1;
+      if (p < s.hoff_prob) {           // generateHoffNewEvent, EventGen.hs:94-109
+        const double d2 = rng.exponential(s.call_dur);
+        const int mm = c_tab.n2cnt[cell];
+        const int to = c_tab.n2list[cell][rng.uniform_int(mm)];
+        q_push_end(s, q, cell, CH_NONE_YET, to, __dadd_rn(time, d2));
+        q.next_id++;  // the HOFF event's id (pushed right after its END, never stored)
+      } else {                         // generateEndEvent, EventGen.hs:111-112
+        const double d2 = rng.exponential(s.call_dur);
+        q_push_end(s, q, cell, CH_NONE_YET, HOFF_NONE, __dadd_rn(time, d2));
+      }
+    }
+  } else if (type == EV_HOFF) {
+    if (accepted) {                    // generateHoffEndEvent, EventGen.hs:114-116
+      const double d2 = rng.exponential(s.call_dur_hoff);
+      pend = QNEW + q.n_end < (unsigned)QCAP ? (int)(QNEW + q.n_end) : -1;
+      q_push_end(s, q, cell, CH_NONE_YET, HOFF_NONE, __dadd_rn(time, d2));
+    }
+  }
+  __syncwarp();
+  // the next event (Simulator.hs:132-134)
+  if (type == EV_END && ev_hoff != HOFF_NONE) {
+    if (lane == 0) {  // the HOFF that follows a hand-off END: same time, next id
+      s.ev_type = EV_HOFF;
+      s.ev_cell = ev_hoff;
+      s.ev_ch = -1;
+      s.ev_hoff = HOFF_NONE;
+    }
+  } else {
+    q_pop(s, q, &pend);
+  }
+  if (lane == 0) {
+    t.pend_slot = pend;
+    t.q_n_end = q.n_end;
+    t.q_overflow = q.overflow ? 1 : 0;
+    t.rng_ndraws = rng.ndraws;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void env_post(Smem& sm, const int act) {
+  RepState& s = sm.s;
+  Scratch& t = sm.t;
+  const int lane = lane_id();
+  const int type = t.cur_type, cell = t.ev_cell, ev_ch = t.cur_ch;
+  if (lane == 0) {
+    if (t.pend_slot >= 0) s.q_key[t.pend_slot] = (uint16_t)((cell << 7) | act);
+    else if (s.ev_type == EV_END && s.ev_ch == CH_NONE_YET) s.ev_ch = act;  // the call accepted just now ends before anything else happens
+  }
+  __syncwarp();
+  if (type == EV_END && act >= 0 && act != ev_ch) {
+    // END toCh, Simulator.hs:129-130: reassign cell act -> ev_ch (EventGen.hs:62-72): the call that used `act` continues
+    // on ev_ch, so its END event is re-keyed -- in the queue, or in s.ev_* when it is the event just popped
+    const bool popped = s.ev_type == EV_END && s.ev_cell == cell && s.ev_ch == act;  // uniform
+    __syncwarp();
+    if (popped) {
+      if (lane == 0) s.ev_ch = ev_ch;
+    } else {
+      QRegs qq{t.q_n_end, 0u, false};
+      q_reassign(s, qq, cell, act, ev_ch);
+    }
   }
   __syncwarp();
 }
@@ -1129,8 +1240,10 @@ __device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a
     if (it >= a.max_events || s.status != ST_RUNNING) break;  // uniform
     const int n = t.ncand;
     const bool is_end = t.ev_is_end;
-    const bool la = a.lookahead && is_end && n > 0 && s.ev_hoff != HOFF_NONE;  // uniform: the departure half of a hand-off
-    if (la) lookahead_folds(sm, m, n, t.ev_cell, s.ev_hoff);
+    const int cur_hoff = t.cur_hoff;
+    const bool la = a.lookahead && is_end && n > 0 && cur_hoff != HOFF_NONE;  // uniform: the departure half of a hand-off
+    if (wid == 3) env_ahead(sm, q, rng, n > 0);  // (warp 3 holds no fold: at most 70 candidates, 30 + 32 + 32 lanes on warps 0-2)
+    if (la) lookahead_folds(sm, m, n, t.ev_cell, cur_hoff);
     else ref_folds(sm, m, n, is_end);
     __syncthreads();
     DCA_RCLK(1)
@@ -1166,7 +1279,7 @@ __device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a
     __syncthreads();  // the decision and the scalars of the update are published
     DCA_RCLK(2)
     if (wid == 0) {
-      environment_step(s, q, rng, act);  // Simulator.hs:101-134
+      env_post(sm, act);
       int stop = ST_RUNNING;
       if (lane == 0) {
         const float td = t.loss;
@@ -1177,7 +1290,7 @@ __device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a
           s.loss_sum = __fadd_rn(s.loss_sum, td);
           s.loss_n += 1;
         }
-        if (stop == ST_RUNNING && q.overflow) stop = ST_QUEUE_OVERFLOW;
+        if (stop == ST_RUNNING && t.q_overflow) stop = ST_QUEUE_OVERFLOW;
       }
       stop = __shfl_sync(0xffffffffu, stop, 0);
       if (stop == ST_RUNNING && (a.verify_rc || a.verify_nb)) {
@@ -1187,15 +1300,15 @@ __device__ __forceinline__ void run_events_overlapped(Smem& sm, const RunArgs& a
       if (lane == 0) {
         if (stop == ST_RUNNING && s.min_loss > 0.0f && s.iter > 50 && fabsf(t.loss) < s.min_loss) stop = ST_ZERO_LOSS;
         if (stop == ST_RUNNING && s.iter == s.n_events) stop = ST_SUCCESS;
-        if (stop == ST_RUNNING && a.rng_mode == RNG_TAPE && rng.ndraws + 8 > rng.tape_len) stop = ST_TAPE_EXHAUSTED;
+        if (stop == ST_RUNNING && a.rng_mode == RNG_TAPE && t.rng_ndraws + 8 > rng.tape_len) stop = ST_TAPE_EXHAUSTED;
         s.status = stop;
       }
       stop = __shfl_sync(0xffffffffu, stop, 0);
       if (stop == ST_RUNNING && it + 1 < a.max_events) ref_prepare_event(sm);  // (does not touch what the update reads)
-    } else {
-      // accFn2's dense part: weight / gradient-correction update (and the next event's products)
-      ref_update_rows<true, 96>(sm, m, (int)threadIdx.x - 32);
     }
+    // accFn2's dense part: weight / gradient-correction update (and the next event's products); warp 0 joins with its
+    // share of the rows once its tail is done
+    ref_update_rows<true, 128>(sm, m, (int)threadIdx.x);
   }
 }
 
@@ -1225,7 +1338,7 @@ __global__ void __launch_bounds__(128, 4) k_run(RunArgs a) {
   } else {
     run_events_overlapped(sm, a, q, rng, m);
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == (TRACE ? 0u : 96u)) {  // (the queue counters and the random source live on warp 0 / on warp 3: env_ahead)
     sm.s.n_end = q.n_end;
     sm.s.next_id = q.next_id;
     sm.s.ndraws = rng.ndraws;
