@@ -9,9 +9,10 @@
 // channels, argmax, grid/frep update, event queue, RNG, stats); one LANE per dense right
 // fold (candidates, V(s), x.wGradCorr -- all of an event in lock step on one warp, see
 // ref_fold_lane); the elementwise TDC update by rows of the padded layout.  The run kernel
-// keeps wNet and wGradCorr in global memory (four CTAs per SM) and runs warp 0's tail of an
-// event next to its update (run_events_overlapped); the step kernel and the TRACE
-// instantiation keep the plain sequence.  Reference: runStep, src/SimRunner.hs:60-97.
+// keeps wNet and wGradCorr in global memory (four CTAs per SM) and runs environmentStep next
+// to the folds (env_ahead, warp 3) and the rest of warp 0's tail next to the update
+// (run_events_overlapped); the step kernel and the TRACE instantiation keep the plain
+// sequence.  Reference: runStep, src/SimRunner.hs:60-97.
 //
 // All parity-critical fp32/fp64 arithmetic uses explicit round-to-nearest
 // intrinsics (never contracted); the file is also compiled with -fmad=false.
