@@ -21,7 +21,8 @@ with Replicas(Opt(n_replicas=n_rep, n_events=warm + n_ev, order="ref", rng="phil
     ms = s.run(n_ev)
     h.dca_debug_ref_phase(out, 1)
     print(f"ref {n_rep} x {n_ev}: {ms:.2f} ms, {n_rep*n_ev/ms/1e3:.2f} M events/s")
-    # (thread 0 stamps: it sits on warp 0, which runs environmentStep / stop rules / next candidates next to the update)
-    names = ["folds", "decision", "environmentStep + next candidates (warp 0) + wait for the update"]
+    # (thread 0 stamps: it sits on warp 0, which folds, decides, then runs env_post / stop rules / next candidates and its
+    #  share of the update; env_ahead runs on warp 3 during the folds)
+    names = ["folds (|| env_ahead)", "decision", "env_post + stop rules + next candidates + update"]
     v = [out[i] / (n_rep * n_ev) for i in (1, 2, 3)]
     print("cycles per event:", "  ".join(f"{n} {x:7.0f}" for n, x in zip(names, v)), f"  sum {sum(v):7.0f}")
